@@ -1,0 +1,159 @@
+/*
+ * piqmc_b200.h -- C ABI of libpiqmc_b200.so, the B200 (sm_100a) implementation of the
+ * Metropolis-sweep hot path of hadsed/pathintegral-qmc.
+ *
+ * The reference has no FFI of its own: its "plugin API" is the Python call signature of the
+ * Cython functions in piqmc/qmc.pyx, piqmc/sa.pyx and piqmc/tools.pyx.  The entry points below
+ * are what a thin Python (ctypes) replacement of those modules binds; the reference function
+ * each one stands in for is cited as file:line.  INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative PIQMC_E* code otherwise;
+ *     piqmc_last_error() returns a thread-local message for the last failure;
+ *   - plain pointers and sizes only; all pointers are HOST pointers unless the name says dev;
+ *   - the caller owns every buffer it passes; the library keeps no host pointer after return;
+ *   - a handle owns one CUDA device, one stream and all device buffers; calls on one handle
+ *     must not overlap in time (use one handle per thread / per GPU).
+ *
+ * Spin / bit convention (piqmc/tools.pyx:20-26): bit 0 <-> spin +1, bit 1 <-> spin -1.
+ *
+ * Packed state ("words"): uint64 word[row][spin]; bit `lane` of a word is
+ *   - quantum annealing: Trotter slice `lane` of replica `row`        (lanes = P <= 64)
+ *   - simulated annealing: replica `row*64 + lane`                    (lanes = 64)
+ */
+#ifndef PIQMC_B200_H
+#define PIQMC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PIQMC_OK            0
+#define PIQMC_EINVAL       -1   /* bad argument (-> ValueError)                         */
+#define PIQMC_EZERODIV     -2   /* slices*temp == 0 or temp == 0 (-> ZeroDivisionError,  */
+                                /*   as piqmc/qmc.c:2065-2074,2407-2416)                 */
+#define PIQMC_ECUDA        -3   /* CUDA runtime failure (-> RuntimeError)                */
+#define PIQMC_ENOGRAPH     -4   /* piqmc_set_graph has not been called                   */
+#define PIQMC_ENOSTATE     -5   /* no packed state resident                              */
+#define PIQMC_ENOMEM       -6
+
+typedef struct piqmc_ctx *piqmc_handle;
+
+/* State of glibc's rand() (TYPE_3 additive feedback generator): what the reference consumes
+ * through libc rand() at piqmc/qmc.pyx:132 and piqmc/sa.pyx:116.  f/b are the front and rear
+ * indices into r[]. */
+typedef struct {
+    uint32_t r[31];
+    int32_t f, b;
+} piqmc_rand_state;
+
+/* ---- library / device ---------------------------------------------------------------- */
+int         piqmc_version(void);
+const char *piqmc_last_error(void);
+int         piqmc_device_count(int *count);
+int         piqmc_create(int device, piqmc_handle *out);
+int         piqmc_destroy(piqmc_handle h);
+int         piqmc_synchronize(piqmc_handle h);
+/* the handle's cudaStream_t, for callers that want to record their own events on it */
+void       *piqmc_stream(piqmc_handle h);
+/* number of kernel launches this handle has issued so far */
+uint64_t    piqmc_launch_count(piqmc_handle h);
+
+/* ---- glibc rand() restated on the host (seeding helper for the deterministic paths) ---- */
+void    piqmc_rand_seed(piqmc_rand_state *s, unsigned int seed);     /* == srand(seed)       */
+int32_t piqmc_rand_next(piqmc_rand_state *s);                        /* == rand()            */
+/* copy the process-global libc generator into *s / load *s back into it (glibc only) */
+int     piqmc_rand_capture_libc(piqmc_rand_state *s);
+int     piqmc_rand_restore_libc(const piqmc_rand_state *s);
+
+/* ---- graph ---------------------------------------------------------------------------
+ * The neighbour table of tools.GenerateNeighbors (piqmc/tools.pyx:74-96), split into its two
+ * planes: idx[i*maxnb+n] = (int)nbs[i,n,0], J[i*maxnb+n] = nbs[i,n,1] (float64; the kernels
+ * narrow it to float32 exactly as piqmc/qmc.pyx:106 does, the energy reduction keeps float64).
+ * color[i] in [0,ncolors) is a proper colouring of the graph (ignoring self entries and
+ * zero couplings); it may be NULL when only the deterministic paths are used. */
+int piqmc_set_graph(piqmc_handle h, int nspins, int maxnb, const int32_t *idx, const double *J,
+                    int ncolors, const int32_t *color);
+
+/* ---- deterministic, reference-stream paths (bit-exact) --------------------------------
+ * One replica per GPU thread, each replaying the reference's sequential algorithm with the
+ * reference's random streams:
+ *   perms[(r*nsweeps + sweep)*nspins + t]  the spin order of sweep `sweep` of replica r, i.e. the
+ *        successive results of rng.permutation (piqmc/qmc.pyx:90-91,136), nsweeps = nsched*mcsteps;
+ *   rstate[r]   glibc rand() state of replica r, advanced in place (lazy consumption,
+ *        piqmc/qmc.pyx:130-133); or, if uniforms != NULL, uniforms[r*nuniforms + c] is the c-th
+ *        value of rand()/RAND_MAX for replica r and rstate may be NULL;
+ *   consumed[r] receives the number of uniforms replica r drew (may be NULL).
+ * spins are +-1 int8, modified in place.
+ */
+
+/* qmc.QuantumAnneal (piqmc/qmc.pyx:30-136), as shipped, including: float32 running ediff reset
+ * once per slice, Trotter neighbours slices-1 and 1 for every slice, lazy rand().
+ * spins[(r*nspins + i)*slices + k].   jperp is computed on the host by piqmc_jperp. */
+int piqmc_qa_det(piqmc_handle h, const double *sched, int nsched, int mcsteps, int slices,
+                 float temp, int nreplicas, int8_t *spins, const int32_t *perms,
+                 piqmc_rand_state *rstate, const double *uniforms, uint64_t nuniforms,
+                 uint64_t *consumed);
+
+/* sa.Anneal (piqmc/sa.pyx:50-120).  spins[r*nspins + i]. */
+int piqmc_sa_det(piqmc_handle h, const double *sched, int nsched, int mcsteps, int nreplicas,
+                 int8_t *spins, const int32_t *perms, piqmc_rand_state *rstate,
+                 const double *uniforms, uint64_t nuniforms, uint64_t *consumed);
+
+/* sa.Anneal_multispin (piqmc/sa.pyx:282-405): groups of 64 replicas, float64 ediffs, no
+ * ediff>0 shortcut.  words[g*nspins + i]: replica k of group g in bit 63-k (sa.pyx:339-345).
+ * rands[((g*nsweeps + sweep)*nspins + t)*64 + k]: the rng.rand(64) block in force at attempt t. */
+int piqmc_sa_multispin_det(piqmc_handle h, const double *sched, int nsched, int mcsteps,
+                           int ngroups, uint64_t *words, const int32_t *perms,
+                           const double *rands);
+
+/* J_perp(Gamma) with the reference's cast order (piqmc/qmc.pyx:95, piqmc/qmc.c:2063-2075). */
+float piqmc_jperp(double gamma, int slices, float temp);
+
+/* ---- production colour-parallel paths -------------------------------------------------
+ * Packed state resident on the device; Philox4x32-10 keyed by (seed; spin, lane, sweep, row).
+ * Semantics are stated on the CPU in oracle/piqmc_oracle.c part 3 and reproduced bit-exactly.
+ */
+int piqmc_state_alloc(piqmc_handle h, int nrows, int lanes);
+/* random initial state from Philox: tile != 0 -> one bit per (row, spin) copied to every lane
+ * (the reference's np.tile(spinVector,(P,1)).T start, examples/spinglass32.py:94-96);
+ * tile == 0 -> independent bit per (row*64+lane, spin). */
+int piqmc_state_init_random(piqmc_handle h, uint64_t seed, uint32_t row0, int tile);
+/* spins[(row*nspins + i)] +-1, copied to every lane (tile != 0), or
+ * spins[(row*lanes + lane)*nspins + i] (tile == 0) */
+int piqmc_state_upload_spins(piqmc_handle h, const int8_t *spins, int tile);
+int piqmc_state_upload_words(piqmc_handle h, const uint64_t *words);
+int piqmc_state_download_words(piqmc_handle h, uint64_t *words);
+/* device pointer of the packed state / of the last energy result (for NCCL gathers) */
+void *piqmc_state_devptr(piqmc_handle h);
+void *piqmc_energy_devptr(piqmc_handle h);
+
+/* Path-integral QA sweeps over the resident state (lanes = slices).  Colour-class order,
+ * per-spin ediff reset, J_perp recomputed per schedule step.  trotter = 0: neighbours slices-1
+ * and 1 (reference, qmc.pyx:115-117); trotter = 1: periodic k-1,k+1 (requires even slices).
+ * replica0: global id of row 0 (so results do not depend on how replicas are sharded).
+ * Asynchronous on the handle's stream. */
+int piqmc_qa_colour(piqmc_handle h, const double *sched, int nsched, int mcsteps, float temp,
+                    uint64_t seed, uint32_t replica0, uint32_t sweep0, int trotter);
+/* Classical SA sweeps over the resident state (lanes = 64 replicas per word, sa.Anneal rules). */
+int piqmc_sa_colour(piqmc_handle h, const double *sched, int nsched, int mcsteps,
+                    uint64_t seed, uint32_t row0, uint32_t sweep0);
+/* kernel variant selection for piqmc_qa_colour / piqmc_sa_colour: 0 = auto, 1 = generic,
+ * 2 = table-lookup fast path (falls back to generic when the graph does not qualify) */
+int piqmc_set_variant(piqmc_handle h, int variant);
+
+/* sa.ClassicalIsingEnergy (piqmc/sa.pyx:25-44) of every (row, lane) of the resident state,
+ * float64: energies[row*lanes + lane].  energies may be NULL (result stays on the device). */
+int piqmc_energy(piqmc_handle h, double *energies);
+
+/* ClassicalIsingEnergy for host configurations: J given as nnz COO triples holding each bond
+ * once (diagonal = local fields); spins[c*nspins + i] +-1; energies[c]. */
+int piqmc_energy_coo(piqmc_handle h, int nspins, int nnz, const int32_t *row, const int32_t *col,
+                     const double *val, int nconfs, const int8_t *spins, double *energies);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIQMC_B200_H */

@@ -1,0 +1,569 @@
+// api.cu -- the extern "C" surface of libpiqmc_b200.so (include/piqmc_b200.h).
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void piqmc_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+namespace {
+
+// RAII device scratch buffer (freed on every exit path of an API call)
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t n) { return cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)); }
+};
+
+template <typename T>
+void free_dev(T *&p)
+{
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+void free_graph(piqmc_ctx *c)
+{
+    free_dev(c->d_idx);
+    free_dev(c->d_J32);
+    free_dev(c->d_J64);
+    free_dev(c->d_idx_t);
+    free_dev(c->d_J32_t);
+    free_dev(c->d_members);
+    free_dev(c->d_lut);
+    c->color_off.clear();
+    c->nspins = c->maxnb = c->ncolors = 0;
+    c->lut_ok = false;
+}
+
+void free_state(piqmc_ctx *c)
+{
+    free_dev(c->d_words);
+    free_dev(c->d_energy);
+    c->nrows = c->lanes = 0;
+}
+
+int use(piqmc_ctx *c)
+{
+    PIQMC_REQUIRE(c != nullptr, PIQMC_EINVAL, "null handle");
+    PIQMC_CUDA(cudaSetDevice(c->device));
+    return PIQMC_OK;
+}
+
+#define USE(h)                                  \
+    do {                                        \
+        int rc__ = use(h);                      \
+        if (rc__ != PIQMC_OK) return rc__;      \
+    } while (0)
+
+#define TRY(expr)                               \
+    do {                                        \
+        int rc__ = (expr);                      \
+        if (rc__ != PIQMC_OK) return rc__;      \
+    } while (0)
+
+}  // namespace
+
+extern "C" {
+
+int piqmc_version(void) { return 100; }
+
+const char *piqmc_last_error(void) { return g_err; }
+
+int piqmc_device_count(int *count)
+{
+    PIQMC_REQUIRE(count != nullptr, PIQMC_EINVAL, "null count");
+    PIQMC_CUDA(cudaGetDeviceCount(count));
+    return PIQMC_OK;
+}
+
+int piqmc_create(int device, piqmc_handle *out)
+{
+    PIQMC_REQUIRE(out != nullptr, PIQMC_EINVAL, "null out");
+    int n = 0;
+    PIQMC_CUDA(cudaGetDeviceCount(&n));
+    PIQMC_REQUIRE(device >= 0 && device < n, PIQMC_EINVAL, "device %d out of range (have %d)", device, n);
+    PIQMC_CUDA(cudaSetDevice(device));
+    piqmc_ctx *c = new (std::nothrow) piqmc_ctx();
+    PIQMC_REQUIRE(c != nullptr, PIQMC_ENOMEM, "out of host memory");
+    c->device = device;
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        piqmc_set_error("device init failed: %s", cudaGetErrorString(e));
+        delete c;
+        return PIQMC_ECUDA;
+    }
+    c->sm_count = prop.multiProcessorCount;
+    *out = c;
+    return PIQMC_OK;
+}
+
+int piqmc_destroy(piqmc_handle h)
+{
+    if (!h) return PIQMC_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    free_graph(h);
+    free_state(h);
+    free_dev(h->d_epart);
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return PIQMC_OK;
+}
+
+int piqmc_synchronize(piqmc_handle h)
+{
+    USE(h);
+    PIQMC_CUDA(cudaStreamSynchronize(h->stream));
+    return PIQMC_OK;
+}
+
+void *piqmc_stream(piqmc_handle h) { return h ? (void *)h->stream : nullptr; }
+uint64_t piqmc_launch_count(piqmc_handle h) { return h ? h->launches : 0; }
+
+// ---- glibc rand() on the host ---------------------------------------------------------------
+void piqmc_rand_seed(piqmc_rand_state *s, unsigned int seed)
+{
+    // glibc srandom_r for TYPE_3: r[0] = seed (0 -> 1); r[i] = 16807*r[i-1] mod (2^31-1) by
+    // Schrage's method; front = 3, rear = 0; discard 310 outputs.
+    if (seed == 0) seed = 1;
+    s->r[0] = seed;
+    int32_t word = (int32_t)seed;
+    for (int i = 1; i < 31; i++) {
+        long hi = word / 127773, lo = word % 127773;
+        word = (int32_t)(16807 * lo - 2836 * hi);
+        if (word < 0) word += 2147483647;
+        s->r[i] = (uint32_t)word;
+    }
+    s->f = 3;
+    s->b = 0;
+    for (int i = 0; i < 310; i++) (void)piqmc_rand_next(s);
+}
+
+int32_t piqmc_rand_next(piqmc_rand_state *s)
+{
+    uint32_t v = (s->r[s->f] += s->r[s->b]);
+    s->f = (s->f + 1 == 31) ? 0 : s->f + 1;
+    s->b = (s->b + 1 == 31) ? 0 : s->b + 1;
+    return (int32_t)(v >> 1);
+}
+
+#if defined(__GLIBC__)
+// glibc's initstate()/setstate() hand back a pointer to the previous state array whose word 0 is
+// (rear_index * 5 + type) and whose words 1..31 are r[0..30] (stdlib/random_r.c).
+int piqmc_rand_capture_libc(piqmc_rand_state *s)
+{
+    PIQMC_REQUIRE(s != nullptr, PIQMC_EINVAL, "null state");
+    static char scratch[128];
+    int32_t *old = (int32_t *)initstate(1u, scratch, sizeof(scratch));
+    PIQMC_REQUIRE(old != nullptr, PIQMC_EINVAL, "initstate failed");
+    const int type = old[0] % 5, rear = old[0] / 5;
+    int rc = PIQMC_OK;
+    if (type != 3 || rear < 0 || rear >= 31) {
+        piqmc_set_error("libc rand() is not in its default TYPE_3 state (type %d)", type);
+        rc = PIQMC_EINVAL;
+    } else {
+        for (int i = 0; i < 31; i++) s->r[i] = (uint32_t)old[1 + i];
+        s->b = rear;
+        s->f = (rear + 3) % 31;
+    }
+    setstate((char *)old);
+    return rc;
+}
+
+int piqmc_rand_restore_libc(const piqmc_rand_state *s)
+{
+    PIQMC_REQUIRE(s != nullptr && s->b >= 0 && s->b < 31, PIQMC_EINVAL, "bad state");
+    static char scratch[128];
+    int32_t *old = (int32_t *)initstate(1u, scratch, sizeof(scratch));
+    PIQMC_REQUIRE(old != nullptr, PIQMC_EINVAL, "initstate failed");
+    for (int i = 0; i < 31; i++) old[1 + i] = (int32_t)s->r[i];
+    old[0] = s->b * 5 + 3;
+    setstate((char *)old);
+    return PIQMC_OK;
+}
+#else
+int piqmc_rand_capture_libc(piqmc_rand_state *) { piqmc_set_error("glibc only"); return PIQMC_EINVAL; }
+int piqmc_rand_restore_libc(const piqmc_rand_state *) { piqmc_set_error("glibc only"); return PIQMC_EINVAL; }
+#endif
+
+float piqmc_jperp(double gamma, int slices, float temp)
+{
+    // piqmc/qmc.pyx:95 with the casts of piqmc/qmc.c:2063-2075
+    const float t12 = (float)slices * temp;
+    return (float)(((-0.5 * slices) * (double)temp) * log(tanh(gamma / (double)t12)));
+}
+
+// ---- graph --------------------------------------------------------------------------------
+int piqmc_set_graph(piqmc_handle h, int nspins, int maxnb, const int32_t *idx, const double *J,
+                    int ncolors, const int32_t *color)
+{
+    USE(h);
+    PIQMC_REQUIRE(nspins > 0 && maxnb > 0 && idx && J, PIQMC_EINVAL, "bad graph arguments");
+    const size_t ne = (size_t)nspins * maxnb;
+    for (size_t e = 0; e < ne; e++)
+        PIQMC_REQUIRE(idx[e] >= 0 && idx[e] < nspins, PIQMC_EINVAL,
+                      "neighbour index %d out of range at entry %zu", idx[e], e);
+    if (color) {
+        PIQMC_REQUIRE(ncolors > 0, PIQMC_EINVAL, "ncolors must be positive");
+        for (int i = 0; i < nspins; i++) {
+            PIQMC_REQUIRE(color[i] >= 0 && color[i] < ncolors, PIQMC_EINVAL, "color[%d] out of range", i);
+            for (int n = 0; n < maxnb; n++) {
+                const int j = idx[(size_t)i * maxnb + n];
+                if (j != i && J[(size_t)i * maxnb + n] != 0.0)
+                    PIQMC_REQUIRE(color[j] != color[i], PIQMC_EINVAL,
+                                  "improper colouring: spins %d and %d are coupled and share colour %d",
+                                  i, j, color[i]);
+            }
+        }
+    }
+    PIQMC_CUDA(cudaStreamSynchronize(h->stream));
+    free_graph(h);
+
+    std::vector<float> j32(ne), j32t(ne);
+    std::vector<int32_t> idxt(ne);
+    for (int i = 0; i < nspins; i++)
+        for (int n = 0; n < maxnb; n++) {
+            const size_t e = (size_t)i * maxnb + n;
+            j32[e] = (float)J[e];                       // C-float narrowing, qmc.pyx:106
+            j32t[(size_t)n * nspins + i] = j32[e];
+            idxt[(size_t)n * nspins + i] = idx[e];
+        }
+    PIQMC_CUDA(cudaMalloc(&h->d_idx, ne * sizeof(int32_t)));
+    PIQMC_CUDA(cudaMalloc(&h->d_J32, ne * sizeof(float)));
+    PIQMC_CUDA(cudaMalloc(&h->d_J64, ne * sizeof(double)));
+    PIQMC_CUDA(cudaMalloc(&h->d_idx_t, ne * sizeof(int32_t)));
+    PIQMC_CUDA(cudaMalloc(&h->d_J32_t, ne * sizeof(float)));
+    PIQMC_CUDA(cudaMemcpy(h->d_idx, idx, ne * sizeof(int32_t), cudaMemcpyHostToDevice));
+    PIQMC_CUDA(cudaMemcpy(h->d_J32, j32.data(), ne * sizeof(float), cudaMemcpyHostToDevice));
+    PIQMC_CUDA(cudaMemcpy(h->d_J64, J, ne * sizeof(double), cudaMemcpyHostToDevice));
+    PIQMC_CUDA(cudaMemcpy(h->d_idx_t, idxt.data(), ne * sizeof(int32_t), cudaMemcpyHostToDevice));
+    PIQMC_CUDA(cudaMemcpy(h->d_J32_t, j32t.data(), ne * sizeof(float), cudaMemcpyHostToDevice));
+    h->nspins = nspins;
+    h->maxnb = maxnb;
+    if (color) {
+        std::vector<int32_t> members(nspins);
+        h->color_off.assign(ncolors + 1, 0);
+        for (int i = 0; i < nspins; i++) h->color_off[color[i] + 1]++;
+        for (int c = 0; c < ncolors; c++) h->color_off[c + 1] += h->color_off[c];
+        std::vector<int> fill(h->color_off.begin(), h->color_off.end() - 1);
+        for (int i = 0; i < nspins; i++) members[fill[color[i]]++] = i;   // ascending within a class
+        PIQMC_CUDA(cudaMalloc(&h->d_members, (size_t)nspins * sizeof(int32_t)));
+        PIQMC_CUDA(cudaMemcpy(h->d_members, members.data(), (size_t)nspins * sizeof(int32_t),
+                              cudaMemcpyHostToDevice));
+        h->ncolors = ncolors;
+        TRY(build_lut(h));
+    }
+    // a new graph invalidates any resident state
+    free_state(h);
+    return PIQMC_OK;
+}
+
+// ---- deterministic paths ---------------------------------------------------------------------
+static int det_common_checks(piqmc_handle h, const double *sched, int nsched, int mcsteps, int nreplicas,
+                             const void *spins, const int32_t *perms, const piqmc_rand_state *rstate,
+                             const double *uniforms)
+{
+    PIQMC_REQUIRE(h->nspins > 0, PIQMC_ENOGRAPH, "piqmc_set_graph has not been called");
+    PIQMC_REQUIRE(sched && nsched >= 0 && mcsteps >= 0 && nreplicas > 0 && spins && perms, PIQMC_EINVAL,
+                  "bad arguments");
+    PIQMC_REQUIRE(rstate || uniforms, PIQMC_EINVAL, "need either rstate or uniforms");
+    return PIQMC_OK;
+}
+
+int piqmc_qa_det(piqmc_handle h, const double *sched, int nsched, int mcsteps, int slices, float temp,
+                 int nreplicas, int8_t *spins, const int32_t *perms, piqmc_rand_state *rstate,
+                 const double *uniforms, uint64_t nuniforms, uint64_t *consumed)
+{
+    USE(h);
+    TRY(det_common_checks(h, sched, nsched, mcsteps, nreplicas, spins, perms, rstate, uniforms));
+    PIQMC_REQUIRE(slices >= 2, PIQMC_EINVAL, "slices must be >= 2 (the reference reads slice 1)");
+    // ZeroDivisionError conditions of piqmc/qmc.c:2065-2074 and :2407-2416
+    PIQMC_REQUIRE((float)slices * temp != 0.0f && temp != 0.0f, PIQMC_EZERODIV, "float division");
+    const int N = h->nspins;
+    const size_t nsweeps = (size_t)nsched * mcsteps;
+    std::vector<float> jperp(std::max(nsched, 1));
+    for (int f = 0; f < nsched; f++) jperp[f] = piqmc_jperp(sched[f], slices, temp);
+
+    DevBuf<float> d_jperp;
+    DevBuf<int8_t> d_spins;
+    DevBuf<int32_t> d_perms;
+    DevBuf<piqmc_rand_state> d_rs;
+    DevBuf<double> d_uni;
+    DevBuf<unsigned long long> d_cons;
+    const size_t nsp = (size_t)nreplicas * N * slices, npm = (size_t)nreplicas * nsweeps * N;
+    PIQMC_CUDA(d_jperp.alloc(nsched));
+    PIQMC_CUDA(d_spins.alloc(nsp));
+    PIQMC_CUDA(d_perms.alloc(npm));
+    PIQMC_CUDA(d_cons.alloc(nreplicas));
+    PIQMC_CUDA(cudaMemcpyAsync(d_jperp.p, jperp.data(), nsched * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    PIQMC_CUDA(cudaMemcpyAsync(d_spins.p, spins, nsp, cudaMemcpyHostToDevice, h->stream));
+    PIQMC_CUDA(cudaMemcpyAsync(d_perms.p, perms, npm * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    if (uniforms) {
+        PIQMC_CUDA(d_uni.alloc((size_t)nreplicas * nuniforms));
+        PIQMC_CUDA(cudaMemcpyAsync(d_uni.p, uniforms, (size_t)nreplicas * nuniforms * sizeof(double),
+                                   cudaMemcpyHostToDevice, h->stream));
+    } else {
+        PIQMC_CUDA(d_rs.alloc(nreplicas));
+        PIQMC_CUDA(cudaMemcpyAsync(d_rs.p, rstate, (size_t)nreplicas * sizeof(piqmc_rand_state),
+                                   cudaMemcpyHostToDevice, h->stream));
+    }
+    TRY(launch_qa_det(h, d_jperp.p, nsched, mcsteps, slices, temp, nreplicas, d_spins.p, d_perms.p,
+                      uniforms ? nullptr : d_rs.p, uniforms ? d_uni.p : nullptr, nuniforms, d_cons.p));
+    PIQMC_CUDA(cudaMemcpyAsync(spins, d_spins.p, nsp, cudaMemcpyDeviceToHost, h->stream));
+    if (!uniforms)
+        PIQMC_CUDA(cudaMemcpyAsync(rstate, d_rs.p, (size_t)nreplicas * sizeof(piqmc_rand_state),
+                                   cudaMemcpyDeviceToHost, h->stream));
+    if (consumed)
+        PIQMC_CUDA(cudaMemcpyAsync(consumed, d_cons.p, (size_t)nreplicas * sizeof(uint64_t),
+                                   cudaMemcpyDeviceToHost, h->stream));
+    PIQMC_CUDA(cudaStreamSynchronize(h->stream));
+    return PIQMC_OK;
+}
+
+int piqmc_sa_det(piqmc_handle h, const double *sched, int nsched, int mcsteps, int nreplicas,
+                 int8_t *spins, const int32_t *perms, piqmc_rand_state *rstate, const double *uniforms,
+                 uint64_t nuniforms, uint64_t *consumed)
+{
+    USE(h);
+    TRY(det_common_checks(h, sched, nsched, mcsteps, nreplicas, spins, perms, rstate, uniforms));
+    const int N = h->nspins;
+    const size_t nsweeps = (size_t)nsched * mcsteps;
+    std::vector<float> temps(std::max(nsched, 1));
+    for (int t = 0; t < nsched; t++) temps[t] = (float)sched[t];      // sa.pyx:96
+
+    DevBuf<float> d_temps;
+    DevBuf<int8_t> d_spins;
+    DevBuf<int32_t> d_perms;
+    DevBuf<piqmc_rand_state> d_rs;
+    DevBuf<double> d_uni;
+    DevBuf<unsigned long long> d_cons;
+    const size_t nsp = (size_t)nreplicas * N, npm = (size_t)nreplicas * nsweeps * N;
+    PIQMC_CUDA(d_temps.alloc(nsched));
+    PIQMC_CUDA(d_spins.alloc(nsp));
+    PIQMC_CUDA(d_perms.alloc(npm));
+    PIQMC_CUDA(d_cons.alloc(nreplicas));
+    PIQMC_CUDA(cudaMemcpyAsync(d_temps.p, temps.data(), nsched * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    PIQMC_CUDA(cudaMemcpyAsync(d_spins.p, spins, nsp, cudaMemcpyHostToDevice, h->stream));
+    PIQMC_CUDA(cudaMemcpyAsync(d_perms.p, perms, npm * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    if (uniforms) {
+        PIQMC_CUDA(d_uni.alloc((size_t)nreplicas * nuniforms));
+        PIQMC_CUDA(cudaMemcpyAsync(d_uni.p, uniforms, (size_t)nreplicas * nuniforms * sizeof(double),
+                                   cudaMemcpyHostToDevice, h->stream));
+    } else {
+        PIQMC_CUDA(d_rs.alloc(nreplicas));
+        PIQMC_CUDA(cudaMemcpyAsync(d_rs.p, rstate, (size_t)nreplicas * sizeof(piqmc_rand_state),
+                                   cudaMemcpyHostToDevice, h->stream));
+    }
+    TRY(launch_sa_det(h, d_temps.p, nsched, mcsteps, nreplicas, d_spins.p, d_perms.p,
+                      uniforms ? nullptr : d_rs.p, uniforms ? d_uni.p : nullptr, nuniforms, d_cons.p));
+    PIQMC_CUDA(cudaMemcpyAsync(spins, d_spins.p, nsp, cudaMemcpyDeviceToHost, h->stream));
+    if (!uniforms)
+        PIQMC_CUDA(cudaMemcpyAsync(rstate, d_rs.p, (size_t)nreplicas * sizeof(piqmc_rand_state),
+                                   cudaMemcpyDeviceToHost, h->stream));
+    if (consumed)
+        PIQMC_CUDA(cudaMemcpyAsync(consumed, d_cons.p, (size_t)nreplicas * sizeof(uint64_t),
+                                   cudaMemcpyDeviceToHost, h->stream));
+    PIQMC_CUDA(cudaStreamSynchronize(h->stream));
+    return PIQMC_OK;
+}
+
+int piqmc_sa_multispin_det(piqmc_handle h, const double *sched, int nsched, int mcsteps, int ngroups,
+                           uint64_t *words, const int32_t *perms, const double *rands)
+{
+    USE(h);
+    PIQMC_REQUIRE(h->nspins > 0, PIQMC_ENOGRAPH, "piqmc_set_graph has not been called");
+    PIQMC_REQUIRE(sched && nsched >= 0 && mcsteps >= 0 && ngroups > 0 && words && perms && rands,
+                  PIQMC_EINVAL, "bad arguments");
+    const int N = h->nspins;
+    const size_t nsweeps = (size_t)nsched * mcsteps;
+    std::vector<float> temps(std::max(nsched, 1));
+    for (int t = 0; t < nsched; t++) temps[t] = (float)sched[t];      // sa.pyx:349
+    DevBuf<float> d_temps;
+    DevBuf<uint64_t> d_words;
+    DevBuf<int32_t> d_perms;
+    DevBuf<double> d_rands;
+    const size_t nw = (size_t)ngroups * N, npm = (size_t)ngroups * nsweeps * N, nr = npm * 64;
+    PIQMC_CUDA(d_temps.alloc(nsched));
+    PIQMC_CUDA(d_words.alloc(nw));
+    PIQMC_CUDA(d_perms.alloc(npm));
+    PIQMC_CUDA(d_rands.alloc(nr));
+    PIQMC_CUDA(cudaMemcpyAsync(d_temps.p, temps.data(), nsched * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    PIQMC_CUDA(cudaMemcpyAsync(d_words.p, words, nw * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
+    PIQMC_CUDA(cudaMemcpyAsync(d_perms.p, perms, npm * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    PIQMC_CUDA(cudaMemcpyAsync(d_rands.p, rands, nr * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    TRY(launch_sa_multispin_det(h, d_temps.p, nsched, mcsteps, ngroups, d_words.p, d_perms.p, d_rands.p));
+    PIQMC_CUDA(cudaMemcpyAsync(words, d_words.p, nw * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+    PIQMC_CUDA(cudaStreamSynchronize(h->stream));
+    return PIQMC_OK;
+}
+
+// ---- packed state ----------------------------------------------------------------------------
+int piqmc_state_alloc(piqmc_handle h, int nrows, int lanes)
+{
+    USE(h);
+    PIQMC_REQUIRE(h->nspins > 0, PIQMC_ENOGRAPH, "piqmc_set_graph has not been called");
+    PIQMC_REQUIRE(nrows > 0 && nrows <= 65535, PIQMC_EINVAL, "nrows must be in [1, 65535]");
+    PIQMC_REQUIRE(lanes >= 1 && lanes <= 64, PIQMC_EINVAL,
+                  "lanes must be in [1, 64] (the packed path holds all slices of a spin in one 64-bit word)");
+    PIQMC_CUDA(cudaStreamSynchronize(h->stream));
+    free_state(h);
+    PIQMC_CUDA(cudaMalloc(&h->d_words, (size_t)nrows * h->nspins * sizeof(uint64_t)));
+    PIQMC_CUDA(cudaMalloc(&h->d_energy, (size_t)nrows * lanes * sizeof(double)));
+    PIQMC_CUDA(cudaMemsetAsync(h->d_words, 0, (size_t)nrows * h->nspins * sizeof(uint64_t), h->stream));
+    h->nrows = nrows;
+    h->lanes = lanes;
+    return PIQMC_OK;
+}
+
+int piqmc_state_init_random(piqmc_handle h, uint64_t seed, uint32_t row0, int tile)
+{
+    USE(h);
+    PIQMC_REQUIRE(h->d_words, PIQMC_ENOSTATE, "no packed state (call piqmc_state_alloc)");
+    return launch_state_init(h, seed, row0, tile);
+}
+
+int piqmc_state_upload_spins(piqmc_handle h, const int8_t *spins, int tile)
+{
+    USE(h);
+    PIQMC_REQUIRE(h->d_words, PIQMC_ENOSTATE, "no packed state (call piqmc_state_alloc)");
+    PIQMC_REQUIRE(spins, PIQMC_EINVAL, "null spins");
+    const size_t n = (size_t)h->nrows * h->nspins * (tile ? 1 : h->lanes);
+    DevBuf<int8_t> d;
+    PIQMC_CUDA(d.alloc(n));
+    PIQMC_CUDA(cudaMemcpyAsync(d.p, spins, n, cudaMemcpyHostToDevice, h->stream));
+    TRY(launch_pack_spins(h, d.p, tile));
+    PIQMC_CUDA(cudaStreamSynchronize(h->stream));
+    return PIQMC_OK;
+}
+
+int piqmc_state_upload_words(piqmc_handle h, const uint64_t *words)
+{
+    USE(h);
+    PIQMC_REQUIRE(h->d_words, PIQMC_ENOSTATE, "no packed state (call piqmc_state_alloc)");
+    PIQMC_REQUIRE(words, PIQMC_EINVAL, "null words");
+    PIQMC_CUDA(cudaMemcpyAsync(h->d_words, words, (size_t)h->nrows * h->nspins * sizeof(uint64_t),
+                               cudaMemcpyHostToDevice, h->stream));
+    PIQMC_CUDA(cudaStreamSynchronize(h->stream));
+    return PIQMC_OK;
+}
+
+int piqmc_state_download_words(piqmc_handle h, uint64_t *words)
+{
+    USE(h);
+    PIQMC_REQUIRE(h->d_words, PIQMC_ENOSTATE, "no packed state (call piqmc_state_alloc)");
+    PIQMC_REQUIRE(words, PIQMC_EINVAL, "null words");
+    PIQMC_CUDA(cudaMemcpyAsync(words, h->d_words, (size_t)h->nrows * h->nspins * sizeof(uint64_t),
+                               cudaMemcpyDeviceToHost, h->stream));
+    PIQMC_CUDA(cudaStreamSynchronize(h->stream));
+    return PIQMC_OK;
+}
+
+void *piqmc_state_devptr(piqmc_handle h) { return h ? (void *)h->d_words : nullptr; }
+void *piqmc_energy_devptr(piqmc_handle h) { return h ? (void *)h->d_energy : nullptr; }
+
+int piqmc_set_variant(piqmc_handle h, int variant)
+{
+    PIQMC_REQUIRE(h != nullptr && variant >= 0 && variant <= 2, PIQMC_EINVAL, "variant must be 0, 1 or 2");
+    h->variant = variant;
+    return PIQMC_OK;
+}
+
+// ---- production sweeps -----------------------------------------------------------------------
+int piqmc_qa_colour(piqmc_handle h, const double *sched, int nsched, int mcsteps, float temp,
+                    uint64_t seed, uint32_t replica0, uint32_t sweep0, int trotter)
+{
+    USE(h);
+    PIQMC_REQUIRE(h->d_words, PIQMC_ENOSTATE, "no packed state (call piqmc_state_alloc)");
+    PIQMC_REQUIRE(h->ncolors > 0, PIQMC_ENOGRAPH, "graph has no colouring");
+    PIQMC_REQUIRE(sched && nsched >= 0 && mcsteps >= 0, PIQMC_EINVAL, "bad schedule");
+    PIQMC_REQUIRE(trotter == 0 || trotter == 1, PIQMC_EINVAL, "trotter must be 0 or 1");
+    PIQMC_REQUIRE(h->lanes >= 2, PIQMC_EINVAL, "slices must be >= 2");
+    PIQMC_REQUIRE((float)h->lanes * temp != 0.0f && temp != 0.0f, PIQMC_EZERODIV, "float division");
+    const float invT = 1.0f / temp;
+    uint32_t sweep = sweep0;
+    for (int f = 0; f < nsched; f++) {
+        const float jp2 = 2.0f * piqmc_jperp(sched[f], h->lanes, temp);
+        for (int s = 0; s < mcsteps; s++, sweep++)
+            for (int c = 0; c < h->ncolors; c++)
+                TRY(launch_colour_sweep(h, 1, trotter, c, jp2, invT, seed, replica0, sweep));
+    }
+    return PIQMC_OK;
+}
+
+int piqmc_sa_colour(piqmc_handle h, const double *sched, int nsched, int mcsteps, uint64_t seed,
+                    uint32_t row0, uint32_t sweep0)
+{
+    USE(h);
+    PIQMC_REQUIRE(h->d_words, PIQMC_ENOSTATE, "no packed state (call piqmc_state_alloc)");
+    PIQMC_REQUIRE(h->ncolors > 0, PIQMC_ENOGRAPH, "graph has no colouring");
+    PIQMC_REQUIRE(sched && nsched >= 0 && mcsteps >= 0, PIQMC_EINVAL, "bad schedule");
+    uint32_t sweep = sweep0;
+    for (int t = 0; t < nsched; t++) {
+        const float invT = 1.0f / (float)sched[t];
+        for (int s = 0; s < mcsteps; s++, sweep++)
+            for (int c = 0; c < h->ncolors; c++)
+                TRY(launch_colour_sweep(h, 0, 0, c, 0.0f, invT, seed, row0, sweep));
+    }
+    return PIQMC_OK;
+}
+
+// ---- energies --------------------------------------------------------------------------------
+int piqmc_energy(piqmc_handle h, double *energies)
+{
+    USE(h);
+    PIQMC_REQUIRE(h->d_words, PIQMC_ENOSTATE, "no packed state (call piqmc_state_alloc)");
+    TRY(launch_energy(h));
+    if (energies) {
+        PIQMC_CUDA(cudaMemcpyAsync(energies, h->d_energy, (size_t)h->nrows * h->lanes * sizeof(double),
+                                   cudaMemcpyDeviceToHost, h->stream));
+        PIQMC_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    return PIQMC_OK;
+}
+
+int piqmc_energy_coo(piqmc_handle h, int nspins, int nnz, const int32_t *row, const int32_t *col,
+                     const double *val, int nconfs, const int8_t *spins, double *energies)
+{
+    USE(h);
+    PIQMC_REQUIRE(nspins > 0 && nnz >= 0 && nconfs > 0 && spins && energies, PIQMC_EINVAL, "bad arguments");
+    PIQMC_REQUIRE(nnz == 0 || (row && col && val), PIQMC_EINVAL, "null COO arrays");
+    for (int e = 0; e < nnz; e++)
+        PIQMC_REQUIRE(row[e] >= 0 && row[e] < nspins && col[e] >= 0 && col[e] < nspins, PIQMC_EINVAL,
+                      "COO entry %d out of range", e);
+    DevBuf<int32_t> d_row, d_col;
+    DevBuf<double> d_val, d_out;
+    DevBuf<int8_t> d_sp;
+    PIQMC_CUDA(d_row.alloc(nnz));
+    PIQMC_CUDA(d_col.alloc(nnz));
+    PIQMC_CUDA(d_val.alloc(nnz));
+    PIQMC_CUDA(d_out.alloc(nconfs));
+    PIQMC_CUDA(d_sp.alloc((size_t)nconfs * nspins));
+    PIQMC_CUDA(cudaMemcpyAsync(d_row.p, row, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    PIQMC_CUDA(cudaMemcpyAsync(d_col.p, col, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    PIQMC_CUDA(cudaMemcpyAsync(d_val.p, val, nnz * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    PIQMC_CUDA(cudaMemcpyAsync(d_sp.p, spins, (size_t)nconfs * nspins, cudaMemcpyHostToDevice, h->stream));
+    TRY(launch_energy_coo(h, nspins, nnz, d_row.p, d_col.p, d_val.p, nconfs, d_sp.p, d_out.p));
+    PIQMC_CUDA(cudaMemcpyAsync(energies, d_out.p, nconfs * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    PIQMC_CUDA(cudaStreamSynchronize(h->stream));
+    return PIQMC_OK;
+}
+
+}  // extern "C"

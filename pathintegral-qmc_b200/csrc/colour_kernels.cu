@@ -1,0 +1,203 @@
+// colour_kernels.cu -- production colour-parallel Metropolis sweeps on bit-packed state.
+//
+// State: uint64 word[row][spin]; bit `lane` = Trotter slice (QA) or replica-in-group (SA).
+// One thread owns one (row, spin) word of the colour class being updated and walks its lanes;
+// all neighbour words belong to other colour classes and are constant during the launch, so
+// the launch is race-free for any proper colouring.  Semantics: oracle/piqmc_oracle.c part 3
+// (oracle_qa_colour / oracle_sa_colour), reproduced bit-exactly.
+//
+// Bandwidth: per launch each word of the class is read and written once and its neighbour
+// words are read once (mostly from L1/L2): ~0.25 B of HBM traffic per attempt at 64 lanes.
+// The kernel is bound by instruction issue, not by memory.
+#include "common.cuh"
+
+namespace {
+
+// +-2J selected by a bit: bit==0 (spins agree) -> -2J, bit==1 -> +2J.  negJ2 = -2J.
+__device__ __forceinline__ float flip_sign(float negJ2, uint32_t bit)
+{
+    return __int_as_float(__float_as_int(negJ2) ^ (int)(bit << 31));
+}
+
+template <bool QA>
+__device__ __forceinline__ bool metropolis(float e, float invT, uint32_t u)
+{
+    if (QA ? (e > 0.0f) : (e >= 0.0f)) return true;
+    const float x = __fmul_rn(e, invT);
+    if (!(x >= PIQMC_XCUT)) return false;
+    return u < colour_thresh(x);
+}
+
+// ------------------------------------------------------------------------------------------
+// Generic variant: any maxnb, any lane count <= NL.  Phase 1 accumulates the in-slice sums of
+// all lanes in registers (neighbour loop outside, lanes unrolled inside: per-lane order is
+// table order, as the specification requires).  Phase 2 walks the lanes in order, adds the
+// Trotter terms from the *current* word (so slice k >= 2 sees the new bit 1, as in the
+// sequential slice-major order) and applies Metropolis with one Philox block per 4 lanes.
+// ------------------------------------------------------------------------------------------
+template <int NL, bool QA, int TROTTER>
+__global__ void __launch_bounds__(128) colour_sweep_generic(
+    uint64_t *__restrict__ words, int nspins, int maxnb, const int32_t *__restrict__ idx_t,
+    const float *__restrict__ J_t, const int32_t *__restrict__ members, int nmembers, int lanes,
+    float jp2, float invT, uint32_t k0, uint32_t k1, uint32_t row0, uint32_t sweep)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= nmembers) return;
+    const int row = blockIdx.y;
+    const int i = members[m];
+    uint64_t *wrow = words + (size_t)row * nspins;
+    uint64_t w = wrow[i];
+
+    float e[NL];
+#pragma unroll
+    for (int k = 0; k < NL; k++) e[k] = 0.0f;
+    for (int n = 0; n < maxnb; n++) {
+        const int j = idx_t[(size_t)n * nspins + i];
+        const float negJ2 = -2.0f * J_t[(size_t)n * nspins + i];
+        const uint64_t x = (j == i) ? w : (w ^ wrow[j]);
+#pragma unroll
+        for (int k = 0; k < NL; k++)
+            e[k] = __fadd_rn(e[k], flip_sign(negJ2, (uint32_t)(x >> k) & 1u));
+    }
+
+    const float njp2 = -jp2;
+    const uint32_t prow = row0 + (uint32_t)row;
+#pragma unroll
+    for (int pass = 0; pass < ((QA && TROTTER == 1) ? 2 : 1); pass++) {
+#pragma unroll
+        for (int g = 0; g < NL / 4; g++) {
+            if (4 * g < lanes) {
+                const u32x4 rnd = philox4x32_10((uint32_t)i, (uint32_t)g | (PIQMC_STREAM_SWEEP << 16),
+                                                sweep, prow, k0, k1);
+                const uint32_t rr[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int k = 4 * g + q;
+                    if (QA && TROTTER == 1 && (k & 1) != pass) continue;
+                    if (k < lanes) {
+                        float ee = e[k];
+                        if (QA) {
+                            const uint32_t own = (uint32_t)(w >> k) & 1u;
+                            int kl, kr;
+                            if (TROTTER == 1) {
+                                kl = (k == 0) ? lanes - 1 : k - 1;
+                                kr = (k == lanes - 1) ? 0 : k + 1;
+                            } else {
+                                kl = lanes - 1;
+                                kr = 1;
+                            }
+                            const uint32_t bl = (uint32_t)(w >> kl) & 1u;
+                            const uint32_t br = (uint32_t)(w >> kr) & 1u;
+                            ee = __fadd_rn(ee, flip_sign(njp2, own ^ bl));
+                            ee = __fadd_rn(ee, flip_sign(njp2, own ^ br));
+                        }
+                        if (metropolis<QA>(ee, invT, rr[q])) w ^= (1ull << k);
+                    }
+                }
+            }
+        }
+    }
+    wrow[i] = w;
+}
+
+// ------------------------------------------------------------------------------------------
+// state initialisation / packing
+// ------------------------------------------------------------------------------------------
+__global__ void state_init_kernel(uint64_t *words, int nspins, int nrows, int lanes, uint32_t k0,
+                                  uint32_t k1, uint32_t row0, int tile)
+{
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (size_t)nrows * nspins) return;
+    const uint32_t row = (uint32_t)(tid / nspins), i = (uint32_t)(tid % nspins);
+    uint64_t w = 0;
+    if (tile) {
+        const u32x4 r = philox4x32_10(i, PIQMC_STREAM_INIT << 16, 0u, row0 + row, k0, k1);
+        if (r.x >> 31) w = (lanes == 64) ? ~0ull : ((1ull << lanes) - 1ull);
+    } else {
+        for (int l = 0; l < lanes; l++) {
+            const u32x4 r = philox4x32_10(i, PIQMC_STREAM_INIT << 16, 0u, (row0 + row) * 64u + l, k0, k1);
+            w |= (uint64_t)(r.x >> 31) << l;
+        }
+    }
+    words[tid] = w;
+}
+
+__global__ void pack_spins_kernel(uint64_t *words, const int8_t *spins, int nspins, int nrows,
+                                  int lanes, int tile)
+{
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (size_t)nrows * nspins) return;
+    const size_t row = tid / nspins, i = tid % nspins;
+    uint64_t w = 0;
+    if (tile) {
+        if (spins[row * nspins + i] < 0) w = (lanes == 64) ? ~0ull : ((1ull << lanes) - 1ull);
+    } else {
+        for (int l = 0; l < lanes; l++)
+            if (spins[(row * lanes + l) * nspins + i] < 0) w |= 1ull << l;
+    }
+    words[tid] = w;
+}
+
+}  // namespace
+
+int launch_state_init(piqmc_ctx *c, uint64_t seed, uint32_t row0, int tile)
+{
+    const size_t n = (size_t)c->nrows * c->nspins;
+    state_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
+        c->d_words, c->nspins, c->nrows, c->lanes, (uint32_t)seed, (uint32_t)(seed >> 32), row0, tile);
+    c->launches++;
+    PIQMC_CUDA(cudaGetLastError());
+    return PIQMC_OK;
+}
+
+int launch_pack_spins(piqmc_ctx *c, const int8_t *d_spins, int tile)
+{
+    const size_t n = (size_t)c->nrows * c->nspins;
+    pack_spins_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_words, d_spins, c->nspins,
+                                                                         c->nrows, c->lanes, tile);
+    c->launches++;
+    PIQMC_CUDA(cudaGetLastError());
+    return PIQMC_OK;
+}
+
+int launch_colour_sweep_lut(piqmc_ctx *c, int qa, int trotter, int color, float jp2, float invT,
+                            uint64_t seed, uint32_t row0, uint32_t sweep);
+
+template <int NL>
+static int launch_generic(piqmc_ctx *c, int qa, int trotter, const int32_t *members, int nmem,
+                          float jp2, float invT, uint64_t seed, uint32_t row0, uint32_t sweep)
+{
+    dim3 block(128), grid((nmem + 127) / 128, c->nrows);
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#define ARGS c->d_words, c->nspins, c->maxnb, c->d_idx_t, c->d_J32_t, members, nmem, c->lanes, jp2, \
+             invT, k0, k1, row0, sweep
+    if (!qa)
+        colour_sweep_generic<NL, false, 0><<<grid, block, 0, c->stream>>>(ARGS);
+    else if (trotter == 1)
+        colour_sweep_generic<NL, true, 1><<<grid, block, 0, c->stream>>>(ARGS);
+    else
+        colour_sweep_generic<NL, true, 0><<<grid, block, 0, c->stream>>>(ARGS);
+#undef ARGS
+    c->launches++;
+    PIQMC_CUDA(cudaGetLastError());
+    return PIQMC_OK;
+}
+
+int launch_colour_sweep(piqmc_ctx *c, int qa, int trotter, int color, float jp2, float invT,
+                        uint64_t seed, uint32_t row0, uint32_t sweep)
+{
+    const int off = c->color_off[color];
+    const int nmem = c->color_off[color + 1] - off;
+    if (nmem == 0) return PIQMC_OK;
+    const int32_t *members = c->d_members + off;
+    if (c->lanes <= 8) return launch_generic<8>(c, qa, trotter, members, nmem, jp2, invT, seed, row0, sweep);
+    if (c->lanes <= 16) return launch_generic<16>(c, qa, trotter, members, nmem, jp2, invT, seed, row0, sweep);
+    if (c->lanes <= 32) return launch_generic<32>(c, qa, trotter, members, nmem, jp2, invT, seed, row0, sweep);
+    return launch_generic<64>(c, qa, trotter, members, nmem, jp2, invT, seed, row0, sweep);
+}
+
+int build_lut(piqmc_ctx *c)
+{
+    (void)c;
+    return PIQMC_OK;
+}

@@ -1,0 +1,131 @@
+// common.cuh -- shared declarations of libpiqmc_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/piqmc_b200.h"
+
+// ------------------------------------------------------------------------------------------
+// error plumbing (never throw across the C ABI)
+// ------------------------------------------------------------------------------------------
+void piqmc_set_error(const char *fmt, ...);
+
+#define PIQMC_CUDA(call)                                                                   \
+    do {                                                                                   \
+        cudaError_t e__ = (call);                                                          \
+        if (e__ != cudaSuccess) {                                                          \
+            piqmc_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),       \
+                            __FILE__, __LINE__);                                           \
+            return PIQMC_ECUDA;                                                            \
+        }                                                                                  \
+    } while (0)
+
+#define PIQMC_REQUIRE(cond, code, ...)                                                     \
+    do {                                                                                   \
+        if (!(cond)) {                                                                     \
+            piqmc_set_error(__VA_ARGS__);                                                  \
+            return (code);                                                                 \
+        }                                                                                  \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// device context
+// ------------------------------------------------------------------------------------------
+struct piqmc_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t launches = 0;
+
+    // graph (set by piqmc_set_graph)
+    int nspins = 0, maxnb = 0, ncolors = 0;
+    int32_t *d_idx = nullptr;       // [N][maxnb]  row-major, table order (deterministic kernels)
+    float *d_J32 = nullptr;         // [N][maxnb]
+    double *d_J64 = nullptr;        // [N][maxnb]  (energy reduction)
+    int32_t *d_idx_t = nullptr;     // [maxnb][N]  transposed, coalesced over spins (colour kernels)
+    float *d_J32_t = nullptr;       // [maxnb][N]
+    int32_t *d_members = nullptr;   // spins sorted by colour
+    std::vector<int> color_off;     // ncolors+1 offsets into d_members
+    bool lut_ok = false;            // graph qualifies for the table-lookup fast path
+    float *d_lut = nullptr;         // [N][16] in-slice partial sums per neighbour pattern (maxnb<=4)
+
+    // packed state
+    int nrows = 0, lanes = 0;
+    uint64_t *d_words = nullptr;    // [nrows][N]
+    double *d_energy = nullptr;     // [nrows][lanes]
+    double *d_epart = nullptr;      // scratch for the energy reduction
+    size_t epart_elems = 0;
+
+    int variant = 0;
+};
+
+// ------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11), as in oracle/piqmc_oracle.c part 3
+// ------------------------------------------------------------------------------------------
+#define PIQMC_STREAM_SWEEP 0u
+#define PIQMC_STREAM_INIT 1u
+#define PIQMC_XCUT (-22.0f)
+
+struct u32x4 {
+    uint32_t x, y, z, w;
+};
+
+__device__ __forceinline__ u32x4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                               uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0;
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ k1;
+        c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return u32x4{c0, c1, c2, c3};
+}
+
+// Acceptance threshold floor(exp_det(x) * 2^32), saturated; every step one IEEE float32 op.
+// Must stay in lock-step with oracle_colour_thresh().
+__device__ __forceinline__ uint32_t colour_thresh(float x)
+{
+    float t = __fmul_rn(x, 1.44269504088896341f);
+    float n = rintf(t);
+    float f = __fsub_rn(t, n);
+    float p = 1.5403530393381609e-4f;
+    p = __fmaf_rn(p, f, 1.3333558146428443e-3f);
+    p = __fmaf_rn(p, f, 9.6181291076284772e-3f);
+    p = __fmaf_rn(p, f, 5.5504108664821580e-2f);
+    p = __fmaf_rn(p, f, 2.4022650695910071e-1f);
+    p = __fmaf_rn(p, f, 6.9314718055994531e-1f);
+    p = __fmaf_rn(p, f, 1.0f);
+    int bits = __float_as_int(p) + (((int)n) << 23);
+    float s = __fmul_rn(__int_as_float(bits), 4294967296.0f);
+    return __float2uint_rz(s);   // cvt.rzi.u32.f32 saturates at 2^32-1
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel launchers (defined in the *_kernels.cu files)
+// ------------------------------------------------------------------------------------------
+int launch_qa_det(piqmc_ctx *c, const float *d_jperp, int nsched, int mcsteps, int slices, float temp,
+                  int nreplicas, int8_t *d_spins, const int32_t *d_perms, piqmc_rand_state *d_rstate,
+                  const double *d_uniforms, uint64_t nuniforms, unsigned long long *d_consumed);
+int launch_sa_det(piqmc_ctx *c, const float *d_temps, int nsched, int mcsteps, int nreplicas,
+                  int8_t *d_spins, const int32_t *d_perms, piqmc_rand_state *d_rstate,
+                  const double *d_uniforms, uint64_t nuniforms, unsigned long long *d_consumed);
+int launch_sa_multispin_det(piqmc_ctx *c, const float *d_temps, int nsched, int mcsteps, int ngroups,
+                            uint64_t *d_words, const int32_t *d_perms, const double *d_rands);
+
+int launch_state_init(piqmc_ctx *c, uint64_t seed, uint32_t row0, int tile);
+int launch_pack_spins(piqmc_ctx *c, const int8_t *d_spins, int tile);
+// one colour class of one sweep; qa != 0: QA rules with Trotter terms (jp2 = 2*jperp)
+int launch_colour_sweep(piqmc_ctx *c, int qa, int trotter, int color, float jp2, float invT,
+                        uint64_t seed, uint32_t row0, uint32_t sweep);
+int launch_energy(piqmc_ctx *c);
+int launch_energy_coo(piqmc_ctx *c, int nspins, int nnz, const int32_t *d_row, const int32_t *d_col,
+                      const double *d_val, int nconfs, const int8_t *d_spins, double *d_out);
+int build_lut(piqmc_ctx *c);

@@ -1,0 +1,276 @@
+"""Device handle: the host-side object behind piqmc.qmc / piqmc.sa / piqmc.tools.
+
+One `Device` owns one GPU context handle of libpiqmc_b200 (stream, graph tables, packed replica
+state).  The reference has no such object -- it is a set of free functions mutating NumPy
+arrays -- so the drop-in functions in qmc.py / sa.py use a process-wide default Device and this
+class is the explicit, batched interface (R replicas per call).
+"""
+import ctypes
+import hashlib
+
+import numpy as np
+
+from . import _lib
+from ._lib import RandState, check, lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def split_nbs(nbs):
+    """nbs float64[N,maxnb,2] (tools.GenerateNeighbors) -> (idx int32[N,maxnb], J float64[N,maxnb]).
+    idx uses the reference's int(...) truncation (piqmc/qmc.pyx:104)."""
+    nbs = np.asarray(nbs)
+    if nbs.dtype != np.float64:
+        raise ValueError("Buffer dtype mismatch, expected 'float_t' but got '%s'" % nbs.dtype)
+    if nbs.ndim != 3 or nbs.shape[2] != 2:
+        raise ValueError("Buffer has wrong number of dimensions (expected 3, got %d)" % nbs.ndim)
+    idx = np.ascontiguousarray(nbs[:, :, 0].astype(np.int32))
+    J = np.ascontiguousarray(nbs[:, :, 1], dtype=np.float64)
+    return idx, J
+
+
+def rand_states(seeds):
+    """ctypes array of glibc rand() states, one per seed (== srand(seed) in a fresh process)."""
+    arr = (RandState * len(seeds))()
+    for k, s in enumerate(seeds):
+        lib.piqmc_rand_seed(ctypes.byref(arr[k]), int(s) & 0xFFFFFFFF)
+    return arr
+
+
+class DeviceArray:
+    """A device buffer exposed through __cuda_array_interface__ (zero-copy into torch for the
+    final NCCL gather).  The memory belongs to the Device; keep the Device alive."""
+
+    def __init__(self, ptr, shape, typestr, owner):
+        self._owner = owner
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr,
+                                         "data": (int(ptr), False), "version": 2, "strides": None}
+
+
+class Device:
+    def __init__(self, index=0):
+        self._h = ctypes.c_void_p()
+        check(lib.piqmc_create(int(index), ctypes.byref(self._h)))
+        self.index = int(index)
+        self.nspins = 0
+        self.maxnb = 0
+        self.ncolors = 0
+        self.nrows = 0
+        self.lanes = 0
+        self._graph_key = None
+
+    def close(self):
+        if self._h:
+            lib.piqmc_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ misc
+    @property
+    def stream(self):
+        """cudaStream_t (int) all work of this Device is issued on."""
+        return lib.piqmc_stream(self._h)
+
+    @property
+    def launch_count(self):
+        return int(lib.piqmc_launch_count(self._h))
+
+    def synchronize(self):
+        check(lib.piqmc_synchronize(self._h))
+
+    def set_variant(self, variant):
+        check(lib.piqmc_set_variant(self._h, int(variant)))
+
+    # ------------------------------------------------------------------ graph
+    def set_graph(self, nbs, color=None):
+        """Upload the neighbour table (and, for the colour paths, a proper colouring).
+        Cached on content: re-uploading the same table is free."""
+        idx, J = split_nbs(nbs)
+        col = None if color is None else np.ascontiguousarray(color, dtype=np.int32)
+        hsh = hashlib.blake2b(digest_size=16)
+        hsh.update(idx.tobytes())
+        hsh.update(J.tobytes())
+        if col is not None:
+            hsh.update(col.tobytes())
+        key = (idx.shape, hsh.digest())
+        if key == self._graph_key:
+            return
+        ncol = 0 if col is None else int(col.max()) + 1
+        if col is not None and col.shape != (idx.shape[0],):
+            raise ValueError("color must have one entry per spin")
+        check(lib.piqmc_set_graph(self._h, idx.shape[0], idx.shape[1], _ptr(idx), _ptr(J), ncol, _ptr(col)))
+        self.nspins, self.maxnb, self.ncolors = idx.shape[0], idx.shape[1], ncol
+        self.nrows = self.lanes = 0
+        self._graph_key = key
+
+    # ------------------------------------------------------------------ deterministic paths
+    def qa_det(self, sched, mcsteps, slices, temp, spins, perms, rstates=None, uniforms=None):
+        """qmc.QuantumAnneal for R replicas, bit-exact.  spins int8[R,N,P] (in place),
+        perms int32[R,nsweeps,N]; rstates = ctypes array of RandState (advanced in place) or
+        uniforms float64[R,nuni].  Returns consumed uint64[R]."""
+        sched = np.ascontiguousarray(sched, dtype=np.float64)
+        R = spins.shape[0]
+        self._check_det(spins, (R, self.nspins, slices), perms, (R, sched.size * mcsteps, self.nspins))
+        consumed = np.zeros(R, dtype=np.uint64)
+        uni, nuni = self._uniforms(uniforms, R)
+        check(lib.piqmc_qa_det(self._h, _ptr(sched), sched.size, int(mcsteps), int(slices),
+                               ctypes.c_float(temp), R, _ptr(spins), _ptr(perms),
+                               None if rstates is None else ctypes.cast(rstates, ctypes.c_void_p),
+                               _ptr(uni), nuni, _ptr(consumed)))
+        return consumed
+
+    def sa_det(self, sched, mcsteps, spins, perms, rstates=None, uniforms=None):
+        """sa.Anneal for R replicas, bit-exact.  spins int8[R,N] in place."""
+        sched = np.ascontiguousarray(sched, dtype=np.float64)
+        R = spins.shape[0]
+        self._check_det(spins, (R, self.nspins), perms, (R, sched.size * mcsteps, self.nspins))
+        consumed = np.zeros(R, dtype=np.uint64)
+        uni, nuni = self._uniforms(uniforms, R)
+        check(lib.piqmc_sa_det(self._h, _ptr(sched), sched.size, int(mcsteps), R, _ptr(spins), _ptr(perms),
+                               None if rstates is None else ctypes.cast(rstates, ctypes.c_void_p),
+                               _ptr(uni), nuni, _ptr(consumed)))
+        return consumed
+
+    def sa_multispin_det(self, sched, mcsteps, words, perms, rands):
+        """sa.Anneal_multispin for G groups of 64 replicas.  words uint64[G,N] in place,
+        perms int32[G,nsweeps,N], rands float64[G,nsweeps*N,64]."""
+        sched = np.ascontiguousarray(sched, dtype=np.float64)
+        G = words.shape[0]
+        nsw = sched.size * mcsteps
+        if words.dtype != np.uint64 or not words.flags.c_contiguous or words.shape != (G, self.nspins):
+            raise ValueError("words must be C-contiguous uint64[G,N]")
+        if perms.dtype != np.int32 or not perms.flags.c_contiguous or perms.shape != (G, nsw, self.nspins):
+            raise ValueError("perms must be C-contiguous int32[G,nsweeps,N]")
+        rands = np.ascontiguousarray(rands, dtype=np.float64)
+        if rands.size != G * nsw * self.nspins * 64:
+            raise ValueError("rands must hold 64 doubles per attempt")
+        check(lib.piqmc_sa_multispin_det(self._h, _ptr(sched), sched.size, int(mcsteps), G, _ptr(words),
+                                         _ptr(perms), _ptr(rands)))
+
+    def _check_det(self, spins, sshape, perms, pshape):
+        if self.nspins == 0:
+            raise ValueError("set_graph has not been called")
+        if spins.dtype != np.int8 or not spins.flags.c_contiguous or spins.shape != sshape:
+            raise ValueError("spins must be C-contiguous int8 of shape %s" % (sshape,))
+        if perms.dtype != np.int32 or not perms.flags.c_contiguous or perms.shape != pshape:
+            raise ValueError("perms must be C-contiguous int32 of shape %s" % (pshape,))
+        if perms.size and (perms.min() < 0 or perms.max() >= self.nspins):
+            raise ValueError("perms entries out of range")
+
+    @staticmethod
+    def _uniforms(uniforms, R):
+        if uniforms is None:
+            return None, 0
+        u = np.ascontiguousarray(uniforms, dtype=np.float64)
+        if u.ndim != 2 or u.shape[0] != R:
+            raise ValueError("uniforms must be float64[R,nuni]")
+        return u, u.shape[1]
+
+    # ------------------------------------------------------------------ packed state
+    def state_alloc(self, nrows, lanes):
+        check(lib.piqmc_state_alloc(self._h, int(nrows), int(lanes)))
+        self.nrows, self.lanes = int(nrows), int(lanes)
+
+    def state_init_random(self, seed, row0=0, tile=True):
+        check(lib.piqmc_state_init_random(self._h, int(seed), int(row0), 1 if tile else 0))
+
+    def state_upload_spins(self, spins, tile=True):
+        """tile: spins int8[nrows,N] copied to every lane; else int8[nrows,lanes,N]."""
+        spins = np.ascontiguousarray(spins, dtype=np.int8)
+        want = (self.nrows, self.nspins) if tile else (self.nrows, self.lanes, self.nspins)
+        if spins.shape != want:
+            raise ValueError("spins must have shape %s" % (want,))
+        check(lib.piqmc_state_upload_spins(self._h, _ptr(spins), 1 if tile else 0))
+
+    def state_upload_words(self, words):
+        words = np.ascontiguousarray(words, dtype=np.uint64)
+        if words.shape != (self.nrows, self.nspins):
+            raise ValueError("words must have shape (nrows, nspins)")
+        check(lib.piqmc_state_upload_words(self._h, _ptr(words)))
+
+    def state_download_words(self, out=None):
+        if out is None:
+            out = np.empty((self.nrows, self.nspins), dtype=np.uint64)
+        check(lib.piqmc_state_download_words(self._h, _ptr(out)))
+        return out
+
+    def state_download_spins(self):
+        """int8[nrows, lanes, N] of +-1 (host-side unpack of the packed words)."""
+        w = self.state_download_words()
+        lanes = np.arange(self.lanes, dtype=np.uint64)
+        bits = (w[:, None, :] >> lanes[None, :, None]) & np.uint64(1)
+        return (1 - 2 * bits.astype(np.int8)).astype(np.int8)
+
+    def state_device_array(self):
+        return DeviceArray(lib.piqmc_state_devptr(self._h), (self.nrows, self.nspins), "<u8", self)
+
+    def energy_device_array(self):
+        return DeviceArray(lib.piqmc_energy_devptr(self._h), (self.nrows, self.lanes), "<f8", self)
+
+    # ------------------------------------------------------------------ production sweeps
+    def qa_colour(self, sched, mcsteps, temp, seed, replica0=0, sweep0=0, trotter=0):
+        """Asynchronous: returns once the launches are queued on the Device's stream."""
+        sched = np.ascontiguousarray(sched, dtype=np.float64)
+        check(lib.piqmc_qa_colour(self._h, _ptr(sched), sched.size, int(mcsteps), ctypes.c_float(temp),
+                                  int(seed), int(replica0), int(sweep0), int(trotter)))
+
+    def sa_colour(self, sched, mcsteps, seed, row0=0, sweep0=0):
+        sched = np.ascontiguousarray(sched, dtype=np.float64)
+        check(lib.piqmc_sa_colour(self._h, _ptr(sched), sched.size, int(mcsteps), int(seed), int(row0),
+                                  int(sweep0)))
+
+    # ------------------------------------------------------------------ energies
+    def energy(self, download=True):
+        """ClassicalIsingEnergy of every (row, lane): float64[nrows, lanes]."""
+        if not download:
+            check(lib.piqmc_energy(self._h, None))
+            return None
+        out = np.empty((self.nrows, self.lanes), dtype=np.float64)
+        check(lib.piqmc_energy(self._h, _ptr(out)))
+        return out
+
+    def energy_coo(self, nspins, row, col, val, spins):
+        row = np.ascontiguousarray(row, dtype=np.int32)
+        col = np.ascontiguousarray(col, dtype=np.int32)
+        val = np.ascontiguousarray(val, dtype=np.float64)
+        spins = np.ascontiguousarray(spins, dtype=np.int8)
+        if spins.ndim != 2 or spins.shape[1] != nspins:
+            raise ValueError("spins must be int8[nconfs, nspins]")
+        out = np.empty(spins.shape[0], dtype=np.float64)
+        check(lib.piqmc_energy_coo(self._h, int(nspins), val.size, _ptr(row), _ptr(col), _ptr(val),
+                                   spins.shape[0], _ptr(spins), _ptr(out)))
+        return out
+
+
+_default = {}
+
+
+def default_device(index=0):
+    """Process-wide Device used by the drop-in functions."""
+    d = _default.get(index)
+    if d is None:
+        d = _default[index] = Device(index)
+    return d
+
+
+def device_count():
+    n = ctypes.c_int(0)
+    check(lib.piqmc_device_count(ctypes.byref(n)))
+    return n.value
+
+
+def capture_libc_rand():
+    s = RandState()
+    check(lib.piqmc_rand_capture_libc(ctypes.byref(s)))
+    return s
+
+
+def restore_libc_rand(state):
+    check(lib.piqmc_rand_restore_libc(ctypes.byref(state)))

@@ -1,0 +1,139 @@
+"""piqmc.qmc -- path-integral quantum annealing (Martonak-Santoro-Tosatti, PRB 66, 094203) on B200.
+
+Mirror of the reference module piqmc/qmc.pyx (same names, argument order, in-place behaviour);
+the sweeps run in libpiqmc_b200.so on the GPU.  There is no CPU fallback.
+
+  QuantumAnneal           drop-in, bit-exact replay of qmc.QuantumAnneal (qmc.pyx:30-136)
+  QuantumAnneal_parallel  same signature as the OpenMP variant (qmc.pyx:247-357); runs the
+                          colour-parallel kernel (per-spin ediff, like that variant)
+  QuantumAnnealBatch      R replicas of QuantumAnneal in one launch (deterministic)
+  QuantumAnnealReplicas   production path: R replicas x P slices, bit-packed, colour-parallel,
+                          Philox; the path bench.py measures
+"""
+import ctypes
+
+import numpy as np
+
+from . import device as _dev
+from . import tools as _tools
+from ._lib import RandState, lib
+from .sa import _draw_perms, _f64, _spins_i8
+
+__all__ = ["QuantumAnneal", "QuantumAnneal_parallel", "QuantumAnnealBatch", "QuantumAnnealReplicas",
+           "JPerp"]
+
+TROTTER = {"reference": 0, "periodic": 1, 0: 0, 1: 1}
+
+
+def JPerp(gamma, slices, temp):
+    """J_perp = -PT/2 log(tanh(Gamma/PT)) with the reference's float32/float64 cast order
+    (piqmc/qmc.pyx:95)."""
+    return float(lib.piqmc_jperp(float(gamma), int(slices), ctypes.c_float(temp)))
+
+
+def _check_confs(confs, nspins, slices):
+    confs = _f64(confs, 2, "confs")
+    if confs.shape != (nspins, slices):
+        raise ValueError("confs must have shape (nspins, slices) = (%d, %d), got %s"
+                         % (nspins, slices, confs.shape))
+    return confs
+
+
+def QuantumAnneal(sched, mcsteps, slices, temp, nspins, confs, nbs, rng, device=None):
+    """Path-integral quantum annealing; @confs (float64[nspins, slices] of +-1, any strides) is
+    updated in place.  Bit-exact replay of the reference (piqmc/qmc.pyx:30-136) including its
+    as-shipped behaviour: float32 running energy difference reset once per slice (:134-135),
+    Trotter neighbours `slices-1` and `1` for every slice (:115-117), libc rand() consumed
+    lazily (:130-133; the process-global libc generator is left where the reference would leave
+    it), spin order from @rng.permutation drawn exactly as the reference draws it.
+    Raises ZeroDivisionError when slices*temp == 0, like the reference.  Returns None."""
+    sched = _f64(sched, 1, "sched")
+    nspins, slices, mcsteps = int(nspins), int(slices), int(mcsteps)
+    confs = _check_confs(confs, nspins, slices)
+    d = device or _dev.default_device()
+    d.set_graph(nbs)
+    if nspins != d.nspins:
+        raise ValueError("nspins=%d but nbs describes %d spins" % (nspins, d.nspins))
+    perms = _draw_perms(rng, nspins, sched.size * mcsteps)[None]
+    spins = np.ascontiguousarray(_spins_i8(confs, "confs"))[None].copy()
+    st = (RandState * 1)()
+    st[0] = _dev.capture_libc_rand()
+    d.qa_det(sched, mcsteps, slices, temp, spins, np.ascontiguousarray(perms), rstates=st)
+    _dev.restore_libc_rand(st[0])
+    confs[:, :] = spins[0]
+    return None
+
+
+def QuantumAnnealBatch(sched, mcsteps, slices, temp, nspins, confs, nbs, rngs, srand_seeds, device=None):
+    """R independent QuantumAnneal runs in one launch (deterministic, bit-exact per replica).
+    confs: [R, nspins, slices] (+-1, float64 or int8); rngs: one RandomState per replica;
+    srand_seeds: the libc seed each replica's own process would have used.
+    Returns (final int8[R,nspins,slices], consumed uint64[R])."""
+    sched = np.ascontiguousarray(sched, dtype=np.float64)
+    d = device or _dev.default_device()
+    d.set_graph(nbs)
+    spins = np.ascontiguousarray(_spins_i8(np.asarray(confs), "confs")).copy()
+    R = spins.shape[0]
+    if spins.shape != (R, nspins, slices):
+        raise ValueError("confs must have shape (R, nspins, slices)")
+    perms = np.stack([_draw_perms(rng, nspins, sched.size * int(mcsteps)) for rng in rngs])
+    st = _dev.rand_states(srand_seeds)
+    consumed = d.qa_det(sched, int(mcsteps), int(slices), temp, spins, perms, rstates=st)
+    return spins, consumed
+
+
+def QuantumAnneal_parallel(sched, mcsteps, slices, temp, nspins, confs, nbs, nthreads=1, device=None,
+                           trotter="reference"):
+    """Same signature as the reference's OpenMP variant (piqmc/qmc.pyx:247-357): per-spin energy
+    difference, no rng argument (uniforms ultimately come from the process-global libc stream:
+    two rand() calls seed Philox), Trotter neighbours slices-1 and 1.  The reference runs spins
+    of a slice concurrently with data races; here the same per-spin rule is applied colour class
+    by colour class on the GPU, race-free.  @nthreads is accepted and ignored.  In place."""
+    sched = _f64(sched, 1, "sched")
+    confs = _check_confs(confs, int(nspins), int(slices))
+    libc = ctypes.CDLL(None)
+    seed = (libc.rand() << 31) | libc.rand()
+    out = QuantumAnnealReplicas(sched, mcsteps, slices, temp, nspins,
+                                np.ascontiguousarray(_spins_i8(confs, "confs").T)[None], nbs, seed,
+                                device=device, trotter=trotter, energies=False, tile=False)
+    confs[:, :] = _tools.UnpackWords(out["words"], int(slices))[0].T
+    return None
+
+
+def QuantumAnnealReplicas(sched, mcsteps, slices, temp, nspins, spins0, nbs, seed, color=None,
+                          replica0=0, trotter="reference", device=None, energies=True, tile=True,
+                          nreplicas=None, download=True):
+    """Production PIQMC: R replicas x `slices` Trotter slices x nspins, one uint64 word per
+    (replica, spin) holding all slices, colour-class Metropolis sweeps with Philox4x32-10 keyed by
+    (seed; spin, slice, sweep, replica0 + r), J_perp recomputed per schedule step.
+
+    spins0: int8[R, nspins] copied to every slice (tile=True, the reference's
+            np.tile(spinVector, (P,1)).T start), or int8[R, slices, nspins] (tile=False), or None
+            for a Philox-generated random start (give nreplicas).
+    Returns dict(words=uint64[R,nspins] (bit k <-> slice k, set <-> spin -1),
+                 energies=float64[R,slices] ClassicalIsingEnergy of every slice)."""
+    sched = np.ascontiguousarray(sched, dtype=np.float64)
+    slices = int(slices)
+    if not 2 <= slices <= 64:
+        raise ValueError("the packed colour path supports 2 <= slices <= 64 (got %d)" % slices)
+    d = device or _dev.default_device()
+    if color is None:
+        color = _tools.ColourGraph(nbs)
+    d.set_graph(nbs, color)
+    if int(nspins) != d.nspins:
+        raise ValueError("nspins=%d but nbs describes %d spins" % (nspins, d.nspins))
+    R = int(nreplicas) if spins0 is None else int(np.asarray(spins0).shape[0])
+    d.state_alloc(R, slices)
+    if spins0 is None:
+        d.state_init_random(seed, replica0, tile=True)
+    else:
+        d.state_upload_spins(spins0, tile=tile)
+    d.qa_colour(sched, int(mcsteps), temp, seed, replica0=replica0, trotter=TROTTER[trotter])
+    out = {"energies": None, "words": None}
+    if energies:
+        out["energies"] = d.energy(download=download)
+    if download:
+        out["words"] = d.state_download_words()
+    else:
+        d.synchronize()
+    return out

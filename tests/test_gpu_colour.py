@@ -1,0 +1,215 @@
+"""GPU parity tests, production colour-parallel paths.
+
+Two levels (BASELINE.json north_star):
+  1. bit-exact: the CUDA kernels on bit-packed state against the CPU statement of the same
+     semantics (oracle/piqmc_oracle.c part 3) -- spins identical, energies <= 1e-12 relative;
+  2. statistical: residual-energy distribution over >= 1000 replicas against the REFERENCE's own
+     per-spin-reset variant qmc.QuantumAnneal_parallel (golden distributions produced by the
+     compiled reference), two-sample KS at p > 0.01.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from helpers import GS_ENERGY, NSPINS, ks_2samp_p
+from test_oracle import _J
+
+pytestmark = pytest.mark.gpu
+
+
+def _graph(golden, inst):
+    import piqmc.tools as T
+    nbs = golden["vec"]["nbs_" + inst]
+    idx, J32 = O.nbs_to_ell(nbs)
+    return nbs, idx, J32, T.ColourGraph(nbs)
+
+
+def _torus(L, seed):
+    import piqmc.tools as T
+    nbs, color = T.GaussianTorusNeighbors(L, seed)
+    idx, J32 = O.nbs_to_ell(nbs)
+    return nbs, idx, J32, color
+
+
+def _qa_both(dev, nbs, idx, J32, color, sched, mcsteps, P, T, R, seed, replica0=0, sweep0=0,
+             trotter=0, variant=0):
+    """Run oracle and device from the same Philox start; return (oracle int8[R,N,P], device same)."""
+    import piqmc.tools as tools
+    n = nbs.shape[0]
+    init = O.colour_init_spins(seed, replica0, R, n)
+    want = np.repeat(init[:, :, None], P, axis=2).copy()
+    O.qa_colour(sched, mcsteps, P, T, idx, J32, color, want, seed, replica0, sweep0, trotter)
+    dev.set_graph(nbs, color)
+    dev.set_variant(variant)
+    dev.state_alloc(R, P)
+    dev.state_init_random(seed, replica0, tile=True)
+    w0 = dev.state_download_words()
+    assert np.array_equal(tools.UnpackWords(w0, P)[:, 0, :], init)       # device init == oracle init
+    import ctypes
+    from piqmc._lib import lib, check
+    s = np.ascontiguousarray(sched, dtype=np.float64)
+    check(lib.piqmc_qa_colour(dev._h, s.ctypes.data_as(ctypes.c_void_p), s.size, mcsteps,
+                              ctypes.c_float(T), seed, replica0, sweep0, trotter))
+    got = tools.UnpackWords(dev.state_download_words(), P)               # [R,P,N]
+    dev.set_variant(0)
+    return want, np.ascontiguousarray(np.transpose(got, (0, 2, 1)))
+
+
+QA_CASES = [
+    # inst, P, T, sched, mcsteps, R
+    ("boixo", 5, 0.01, (0.5, 1e-8, 10), 3, 9),
+    ("boixo", 20, 0.01, (0.5, 1e-8, 10), 3, 5),
+    ("boixo16", 8, 0.05, (1.0, 1e-8, 12), 2, 7),
+    ("bipartite8", 10, 0.01, (8.0, 1e-8, 5), 20, 6),          # maxnb 5, fields, pad rows
+    ("hopfield8", 10, 0.01, (8.0, 1e-8, 5), 20, 6),           # K8: 8 colours, maxnb 8
+    ("inst_0_32x32", 20, 0.01, (1.5, 1e-8, 25), 1, 6),        # config 2 shape
+    ("inst_0_32x32", 64, 0.01, (1.5, 1e-8, 8), 1, 3),         # full 64-lane words
+    ("inst_0_32x32", 33, 0.3, (1.5, 1e-8, 6), 2, 3),          # odd lane count, hot (many draws)
+    ("inst_0_32x32", 2, 0.5, (1.5, 1e-3, 6), 2, 4),           # minimum slices
+    ("santoro_80x80", 20, 0.01, (1.5, 1e-8, 4), 1, 2),        # config 3 shape
+]
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("inst,P,T,sch,mcsteps,R", QA_CASES)
+def test_qa_colour_bit_exact(golden, dev, inst, P, T, sch, mcsteps, R, variant):
+    nbs, idx, J32, color = _graph(golden, inst)
+    sched = np.linspace(*sch[:2], int(sch[2]))
+    want, got = _qa_both(dev, nbs, idx, J32, color, sched, mcsteps, P, T, R, seed=0xC0FFEE + P,
+                         variant=variant)
+    assert np.array_equal(want, got)
+    # device energies of the packed state == ClassicalIsingEnergy per (replica, slice)
+    en = dev.energy()
+    J = _J(golden, inst)
+    ref = np.array([[O.energy(J, got[r, :, k].astype(np.float64)) for k in range(P)] for r in range(R)])
+    np.testing.assert_allclose(en, ref, rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_qa_colour_gaussian_torus_and_offsets(dev, variant):
+    """Config 5's instance family at a size the oracle finishes in seconds; non-zero replica0
+    and sweep0 (sharding / continuation must not change the streams)."""
+    nbs, idx, J32, color = _torus(16, 2024)
+    sched = np.linspace(1.5, 1e-8, 10)
+    want, got = _qa_both(dev, nbs, idx, J32, color, sched, 1, 64, 0.01, 5, seed=2024, replica0=4091,
+                         sweep0=17, variant=variant)
+    assert np.array_equal(want, got)
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_qa_colour_periodic_trotter(golden, dev, variant):
+    nbs, idx, J32, color = _graph(golden, "inst_0_32x32")
+    sched = np.linspace(1.5, 1e-8, 8)
+    for P in (20, 7):
+        want, got = _qa_both(dev, nbs, idx, J32, color, sched, 1, P, 0.05, 3, seed=5, trotter=1,
+                             variant=variant)
+        assert np.array_equal(want, got)
+
+
+def test_qa_colour_sharding_invariance(dev):
+    """Replicas [0,8) in one state == replicas [0,3) and [3,8) run separately with replica0."""
+    import piqmc.qmc as qmc
+    nbs, idx, J32, color = _torus(12, 7)
+    sched = np.linspace(1.5, 1e-8, 6)
+    full = qmc.QuantumAnnealReplicas(sched, 1, 16, 0.01, 144, None, nbs, 99, color=color, nreplicas=8)
+    a = qmc.QuantumAnnealReplicas(sched, 1, 16, 0.01, 144, None, nbs, 99, color=color, nreplicas=3)
+    b = qmc.QuantumAnnealReplicas(sched, 1, 16, 0.01, 144, None, nbs, 99, color=color, nreplicas=5,
+                                  replica0=3)
+    assert np.array_equal(full["words"], np.concatenate([a["words"], b["words"]]))
+    assert np.array_equal(full["energies"], np.concatenate([a["energies"], b["energies"]]))
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("inst,sch,mcsteps,R", [
+    ("boixo", (1.0, 0.01, 10), 3, 70),
+    ("bipartite8", (3.0, 0.01, 10), 2, 64),
+    ("hopfield8", (8.0, 1e-8, 5), 10, 130),
+    ("inst_0_32x32", (3.0, 0.01, 12), 1, 130),
+    ("santoro_80x80", (3.0, 0.01, 3), 1, 65),
+])
+def test_sa_colour_bit_exact(golden, dev, inst, sch, mcsteps, R, variant):
+    import piqmc.sa as sa
+    nbs, idx, J32, color = _graph(golden, inst)
+    n = NSPINS[inst]
+    sched = np.linspace(*sch[:2], int(sch[2]))
+    rng = np.random.RandomState(R)
+    init = (2 * rng.randint(2, size=(R, n)) - 1).astype(np.int8)
+    want = init.copy()
+    O.sa_colour(sched, mcsteps, idx, J32, color, want, seed=31337, row0=2)
+    dev.set_variant(variant)
+    out = sa.AnnealReplicas(sched, mcsteps, init, nbs, 31337, color=color, row0=2, device=dev)
+    dev.set_variant(0)
+    assert np.array_equal(out["spins"], want)
+    J = _J(golden, inst)
+    ref = np.array([O.energy(J, s.astype(np.float64)) for s in want])
+    np.testing.assert_allclose(out["energies"], ref, rtol=1e-12, atol=1e-12)
+
+
+def test_sa_colour_random_start_matches_oracle_init(dev):
+    import piqmc.sa as sa
+    nbs, idx, J32, color = _torus(8, 1)
+    R = 100
+    init = np.concatenate([O.colour_init_spins(5, 64 * g + l, 1, 64) for g in range(2) for l in range(64)])[:R]
+    want = init.copy()
+    sched = np.linspace(3.0, 0.01, 5)
+    O.sa_colour(sched, 1, idx, J32, color, want, seed=5)
+    out = sa.AnnealReplicas(sched, 1, None, nbs, 5, color=color, nreplicas=R, device=dev)
+    assert np.array_equal(out["spins"], want)
+
+
+def test_parallel_signatures_in_place(golden, dev):
+    """qmc.QuantumAnneal_parallel / sa.Anneal_parallel keep the reference's signatures and act in place."""
+    import ctypes
+    import piqmc.qmc as qmc
+    import piqmc.sa as sa
+    nbs = golden["vec"]["nbs_boixo"]
+    J = _J(golden, "boixo")
+    rng = np.random.RandomState(1)
+    ctypes.CDLL(None).srand(3)
+    confs = np.tile(np.array([2 * rng.randint(2) - 1 for _ in range(8)], dtype=np.float64), (5, 1)).T
+    assert qmc.QuantumAnneal_parallel(np.linspace(0.5, 1e-8, 10), 3, 5, 0.01, 8, confs, nbs, 4) is None
+    assert all(sa.ClassicalIsingEnergy(confs[:, k], J) == -8.0 for k in range(5))
+    sv = np.array([2 * rng.randint(2) - 1 for _ in range(8)], dtype=np.float64)
+    assert sa.Anneal_parallel(np.linspace(1.0, 0.01, 10), 3, sv, nbs, 4) is None
+    assert set(np.unique(sv)) <= {-1.0, 1.0}
+
+
+# ------------------------------------------------------------------------------------ statistics
+def _residual(en, inst):
+    return (np.asarray(en) - GS_ENERGY[inst]) / NSPINS[inst]
+
+
+@pytest.mark.parametrize("nsteps", [100, 30])
+def test_qa_colour_residual_energy_distribution_vs_reference(golden, dev, nsteps):
+    """Config 2 (examples/spinglass32.py:58-68): N=1024, P=20, T=0.01, Gamma 1.5->1e-8 in `nsteps`
+    steps, 1024 replicas.  Reference sample: qmc.QuantumAnneal_parallel(nthreads=1), the
+    reference's own per-spin-reset variant (golden, made by the compiled reference).  Statistic:
+    per-replica residual energy per spin, slice-averaged and best-slice.  KS p > 0.01."""
+    import piqmc.qmc as qmc
+    nbs = golden["vec"]["nbs_inst_0_32x32"]
+    ref = golden["dist"]["qa_par_%d" % nsteps]
+    R = ref.shape[0]
+    assert R >= 1000
+    out = qmc.QuantumAnnealReplicas(np.linspace(1.5, 1e-8, nsteps), 1, 20, 0.01, 1024, None, nbs,
+                                    seed=20240 + nsteps, nreplicas=R, device=dev)
+    mine = out["energies"]
+    p_mean = ks_2samp_p(_residual(mine.mean(axis=1), "inst_0_32x32"), _residual(ref.mean(axis=1), "inst_0_32x32"))
+    p_min = ks_2samp_p(_residual(mine.min(axis=1), "inst_0_32x32"), _residual(ref.min(axis=1), "inst_0_32x32"))
+    print("nsteps", nsteps, "residual/spin mine %.4f ref %.4f  KS p(mean) %.3f p(min) %.3f"
+          % (_residual(mine.mean(), "inst_0_32x32"), _residual(ref.mean(), "inst_0_32x32"), p_mean, p_min))
+    assert p_mean > 0.01 and p_min > 0.01
+
+
+@pytest.mark.parametrize("nsteps", [100, 30])
+def test_sa_colour_residual_energy_distribution_vs_reference(golden, dev, nsteps):
+    """sa.Anneal on config 2's pre-anneal schedule shape (3.0 -> 0.01), 1024 replicas, against
+    the reference's sa.Anneal sample.  KS p > 0.01."""
+    import piqmc.sa as sa
+    nbs = golden["vec"]["nbs_inst_0_32x32"]
+    ref = golden["dist"]["sa_%d" % nsteps][:, 0]
+    out = sa.AnnealReplicas(np.linspace(3.0, 0.01, nsteps), 1, None, nbs, seed=777 + nsteps,
+                            nreplicas=ref.shape[0], device=dev)
+    p = ks_2samp_p(_residual(out["energies"], "inst_0_32x32"), _residual(ref, "inst_0_32x32"))
+    print("nsteps", nsteps, "residual/spin mine %.4f ref %.4f KS p %.3f"
+          % (_residual(out["energies"].mean(), "inst_0_32x32"), _residual(ref.mean(), "inst_0_32x32"), p))
+    assert p > 0.01

@@ -1,0 +1,126 @@
+"""CPU tests of the host-side mirror piqmc.tools against the reference's goldens, plus the
+reference's own testing/test_core.py restated."""
+import numpy as np
+import pytest
+import scipy.sparse as sps
+
+import piqmc.tools as tools
+from helpers import NSPINS
+
+
+def test_spinbitconversion():
+    # testing/test_core.py:16-22
+    a = np.array([0., 1., 0., 1., 0., 1., 0., 1., 0., 1.])
+    b = tools.bits2spins(a)
+    c = tools.spins2bits(b)
+    assert np.all(a == [0, 1, 0, 1, 0, 1, 0, 1, 0, 1])
+    assert np.all(b == [1, -1, 1, -1, 1, -1, 1, -1, 1, -1])
+    assert np.all(c == a)
+
+
+def test_generateising():
+    # testing/test_core.py:24-28
+    J = tools.Generate2DIsingInstance(4, np.random.RandomState(123))
+    assert (J - sps.triu(J)).nnz == 0
+
+
+@pytest.mark.parametrize("L,seed", [(4, 123), (6, 7)])
+def test_generateising_matches_reference_draws(golden, L, seed):
+    rng = np.random.RandomState(seed)
+    J = tools.Generate2DIsingInstance(L, rng).tocoo()
+    want = golden["vec"]["gen2d_%d_%d" % (L, seed)]
+    got = np.stack([J.row, J.col, J.data], axis=1)
+    assert np.array_equal(got, want)
+
+
+def _core5():
+    J = sps.dok_matrix((5, 5), dtype=np.float64)
+    for (i, j) in ((0, 1), (1, 2), (2, 3), (3, 4), (0, 3), (1, 4), (0, 4), (0, 0), (1, 1), (2, 2), (3, 3), (4, 4)):
+        J[i, j] = 1
+    return J
+
+
+def test_generateneighbors_core5(golden):
+    """testing/test_core.py:30-81.  The literal in that test encodes Python-2 dict order; on
+    Python 3 the reference itself produces insertion order (stored in the golden).  Check both:
+    identical to the reference's Py3 output, and equal to the Py2 literal row by row as sets."""
+    nb = tools.GenerateNeighbors(nspins=5, J=_core5(), maxnb=4, savepath=None)
+    assert np.array_equal(nb, golden["vec"]["nbs_core5"])
+    true_nb = np.array(
+        [[[1., 1.], [0., 1.], [4., 1.], [3., 1.]],
+         [[0., 1.], [2., 1.], [4., 1.], [1., 1.]],
+         [[1., 1.], [2., 1.], [3., 1.], [0., 0.]],
+         [[3., 1.], [2., 1.], [0., 1.], [4., 1.]],
+         [[4., 1.], [1., 1.], [0., 1.], [3., 1.]]])
+    for i in range(5):
+        assert sorted(map(tuple, nb[i])) == sorted(map(tuple, true_nb[i]))
+    assert np.array_equal(nb[2, 3], [0., 0.])           # pad row stays [0, 0] and comes last
+
+
+@pytest.mark.parametrize("inst", sorted(NSPINS))
+def test_generateneighbors_instances(golden, inst):
+    J = tools.IsingFromTriples(golden["inst"]["inst_" + inst], NSPINS[inst])
+    want = golden["vec"]["nbs_" + inst]
+    nb = tools.GenerateNeighbors(NSPINS[inst], J, want.shape[1])
+    assert nb.dtype == np.float64 and np.array_equal(nb, want)
+
+
+def test_generateneighbors_overflow_and_save(tmp_path, golden):
+    J = tools.IsingFromTriples(golden["inst"]["inst_boixo16"], 16)
+    with pytest.raises(IndexError):
+        tools.GenerateNeighbors(16, J, 4)               # degree 6 > maxnb
+    p = str(tmp_path / "nb.npy")
+    nb = tools.GenerateNeighbors(16, J, 6, p)
+    assert np.array_equal(np.load(p), nb)
+
+
+def test_generateneighbors_other_formats_and_lower_triangle():
+    # santoro_80x80.txt stores some bonds with i > j; CSR input goes through todok()
+    J = sps.dok_matrix((4, 4))
+    J[2, 0] = 0.5
+    J[0, 1] = -1.0
+    J[3, 3] = 0.25
+    nb = tools.GenerateNeighbors(4, J, 2)
+    assert np.array_equal(nb[0], [[2, 0.5], [1, -1.0]])
+    assert np.array_equal(nb[2], [[0, 0.5], [0, 0]])
+    assert np.array_equal(nb[3], [[3, 0.25], [0, 0]])
+    nb2 = tools.GenerateNeighbors(4, J.tocsr(), 2)
+    assert sorted(map(tuple, nb2[0])) == sorted(map(tuple, nb[0]))
+
+
+@pytest.mark.parametrize("inst", sorted(NSPINS))
+def test_colouring_is_proper(golden, inst):
+    nbs = golden["vec"]["nbs_" + inst]
+    color = tools.ColourGraph(nbs)
+    n = nbs.shape[0]
+    for i in range(n):
+        for j, v in nbs[i]:
+            if int(j) != i and v != 0.0:
+                assert color[int(j)] != color[i]
+    ncol = color.max() + 1
+    assert ncol == (8 if inst == "hopfield8" else 2)
+
+
+def test_gaussian_torus_matches_generateneighbors():
+    L = 6
+    nbs, color = tools.GaussianTorusNeighbors(L, 3)
+    rng = np.random.RandomState(3)
+    Jb = rng.standard_normal(size=(L * L, 2)).astype(np.float32).astype(np.float64)
+    J = sps.dok_matrix((L * L, L * L))
+    for i in range(L * L):
+        y, x = divmod(i, L)
+        J[i, y * L + (x + 1) % L] = Jb[i, 0]
+        J[i, ((y + 1) % L) * L + x] = Jb[i, 1]
+    assert np.array_equal(nbs, tools.GenerateNeighbors(L * L, J, 4))
+    assert set(color) == {0, 1}
+    for i in range(L * L):
+        assert all(color[int(j)] != color[i] for j in nbs[i, :, 0])
+
+
+def test_pack_unpack_words():
+    rng = np.random.RandomState(0)
+    s = (2 * rng.randint(2, size=(3, 20, 17)) - 1).astype(np.int8)
+    w = tools.PackWords(s)
+    assert w.shape == (3, 17) and w.dtype == np.uint64
+    assert np.array_equal(tools.UnpackWords(w, 20), s)
+    assert (int(w[1, 5]) >> 7) & 1 == (1 if s[1, 7, 5] < 0 else 0)
