@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- spin-flip attempts/s of the PIQMC Metropolis-sweep hot path on B200.
+
+Workload (BASELINE.json configs[4]): synthetic 256x256 Gaussian torus (J ~ N(0,1) float32,
+RandomState(2024)), P = 64 Trotter slices, R = 4096 replicas in total sharded over the ranks
+(strong scaling, R/N per GPU, no collective on the sweep path), T = 0.01, Gamma linspace(1.5, 1e-8, K).
+One "step" = one schedule step = one Metropolis sweep (mcsteps = 1) over all replicas:
+R*P*N = 1.72e10 attempts.  The production kernel runs the natural-order level colouring, i.e. the
+sweep of the reference's per-spin-reset variant qmc.QuantumAnneal_parallel, whose residual-energy
+statistics it reproduces (tests/test_gpu_colour.py).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (one rank per GPU)
+  python bench.py --impl reference [...]                         the reference's own Cython on host cores
+
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "pathintegral-qmc_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+L, P, R_TOTAL, TEMP = 256, 64, 4096, 0.01
+GAMMA0, GAMMA1 = 1.5, 1e-8
+SEED = 2024
+B_ALG_HBM = 0.25        # bytes/attempt: each 64-slice word read once + written once per sweep
+B_ALG_SMEM = 1.0        # bytes/attempt touched on chip: own r+w, 4 neighbours, 2 Trotter bits
+METRIC = "spin-flip attempts/sec"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks sampling (nvidia-smi during the timed region)
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu = gpu
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU baseline: the reference's own compiled Cython (oracle/_ref) on the host cores
+# ----------------------------------------------------------------------------------------------
+_G = {}
+
+
+def _cpu_init(nbs):
+    from oracle import oracle as O
+    ref = O.ref()
+    if ref is not None:
+        from piqmc_ref import qmc
+        _G["qmc"] = qmc
+    _G["O"] = O
+    _G["nbs"] = nbs
+
+
+def _cpu_job(args):
+    """One replica of config 5 for `nsteps` sweeps on one core; returns seconds."""
+    r, nsteps, kind = args
+    import ctypes
+    n = L * L
+    rng = np.random.RandomState(r)
+    ctypes.CDLL("libc.so.6").srand(r)
+    sv = (2 * rng.randint(2, size=n) - 1).astype(np.float64)
+    confs = np.tile(sv, (P, 1)).T.copy()
+    sched = np.linspace(GAMMA0, GAMMA1, nsteps)
+    t0 = time.perf_counter()
+    if "qmc" in _G:
+        if kind == "qa":
+            _G["qmc"].QuantumAnneal(sched, 1, P, TEMP, n, confs, _G["nbs"], rng)
+        else:
+            _G["qmc"].QuantumAnneal_parallel(sched, 1, P, TEMP, n, confs, _G["nbs"], 1)
+    else:
+        O = _G["O"]
+        if kind == "qa":
+            O.qa_reference(sched, 1, P, TEMP, n, confs, _G["nbs"], O.make_perms(rng, n, nsteps))
+        else:
+            O.qa_parallel1(sched, 1, P, TEMP, n, confs, _G["nbs"])
+    return time.perf_counter() - t0
+
+
+def cpu_rate(nbs, nsteps, kind, cores):
+    """attempts/s of `cores` processes each running one replica for nsteps sweeps (the pattern of
+    examples/spinglass32_mpi.py: independent replicas, one per core)."""
+    from oracle import oracle as O
+    have_ref = O.ref() is not None
+    with mp.Pool(cores, initializer=_cpu_init, initargs=(nbs,)) as pool:
+        pool.map(_cpu_job, [(r, 1, kind) for r in range(cores)])            # warm caches / imports
+        t0 = time.perf_counter()
+        pool.map(_cpu_job, [(r, nsteps, kind) for r in range(cores)])
+        wall = time.perf_counter() - t0
+    return cores * P * L * L * nsteps / wall, wall, ("reference" if have_ref else "port")
+
+
+def run_reference(args):
+    """--impl reference: the reference's qmc.QuantumAnneal (oracle/_ref; the C port if the Cython
+    build is absent) on all host cores, one replica per core, K sweeps of config 5 each."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import piqmc.tools as tools
+    nbs, _ = tools.GaussianTorusNeighbors(L, SEED)
+    cores = os.cpu_count() or 1
+    if args.warmup > 0:
+        cpu_rate(nbs, min(args.warmup, 2), "qa", cores)
+    rate, wall, kind = cpu_rate(nbs, args.steps, "qa", cores)
+    sample = "%d replicas (one per core) x %d sweeps of the 256x256 P=64 workload, qmc.QuantumAnneal" % (cores, args.steps)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "attempts/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(args, cores_note="host cores: %d" % cores),
+        "cpu_baseline": {"value": rate, "unit": "attempts/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": rate, "unit": "attempts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def config_dict(args, cores_note=None):
+    c = {"workload": "synthetic 256x256 Gaussian 2D Ising torus, P=64 slices, R=4096 replicas total, "
+                     "T=0.01, Gamma 1.5->1e-8 over K steps, mcsteps=1 (BASELINE.json configs[4])",
+         "nspins": L * L, "slices": P, "replicas_total": R_TOTAL, "order": args.order,
+         "state": "bit-packed uint64 word per (spin, replica), 2.1 GB total",
+         "l2_policy": "inputs larger than L2: per-GPU state %.0f MB >> 126 MB L2 at N<=8" % (R_TOTAL * L * L * 8 / 1e6 / 8)}
+    if cores_note:
+        c["note"] = cores_note
+    return c
+
+
+# ----------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import piqmc.qmc as qmc
+    import piqmc.tools as tools
+    from piqmc import device
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    assert R_TOTAL % world == 0
+    R = R_TOTAL // world
+    replica0 = rank * R
+    n = L * L
+    K, W = args.steps, args.warmup
+
+    nbs, checker = tools.GaussianTorusNeighbors(L, SEED)
+    color = tools.TorusNaturalLevels(L) if args.order == "natural" else checker
+    dev = device.Device(local)
+    dev.set_variant(args.variant)
+    dev.set_graph(nbs, color)
+    dev.state_alloc(R, P)
+    stream = torch.cuda.ExternalStream(dev.stream, device=torch.device("cuda", local))
+    sched = np.linspace(GAMMA0, GAMMA1, K)
+
+    def barrier():
+        dev.synchronize()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    # ---- warm-up (untimed), then restart from the initial state
+    dev.state_init_random(SEED, replica0, tile=True)
+    if W > 0:
+        dev.qa_colour(np.full(W, GAMMA0), 1, TEMP, SEED, replica0=replica0, sweep0=1 << 30)
+    dev.state_init_random(SEED, replica0, tile=True)
+    barrier()
+
+    # ---- timed region: K schedule steps, device-resident state, CUDA events on the launch stream
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = dev.launch_count
+    barrier()
+    e0.record(stream)
+    dev.qa_colour(sched, 1, TEMP, SEED, replica0=replica0)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = dev.launch_count - l0
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+
+    # ---- final energies on device + the single gather (outside the timed region, reported)
+    tg0 = time.perf_counter()
+    dev.energy(download=False)
+    dev.synchronize()
+    en_local = torch.as_tensor(dev.energy_device_array(), device="cuda")
+    if dist is not None:
+        en_all = torch.empty((world,) + tuple(en_local.shape), dtype=en_local.dtype, device="cuda")
+        dist.all_gather_into_tensor(en_all, en_local.contiguous())
+        en = en_all.reshape(-1, P).cpu().numpy()
+    else:
+        en = en_local.cpu().numpy()
+    gather_ms = 1e3 * (time.perf_counter() - tg0)
+
+    # ---- end to end through the public API with HOST buffers (H2D of the initial spins and
+    #      D2H of packed configurations + energies inside the timed region)
+    rng = np.random.RandomState(SEED + rank)
+    spins0 = (2 * rng.randint(2, size=(R, n)) - 1).astype(np.int8)
+    barrier()
+    t0 = time.perf_counter()
+    out = qmc.QuantumAnnealReplicas(sched, 1, P, TEMP, n, spins0, nbs, SEED, color=color, replica0=replica0,
+                                    device=dev, energies=True, download=True)
+    dev.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    h2d = spins0.nbytes + nbs.size * 4 * 3
+    d2h = out["words"].nbytes + out["energies"].nbytes
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    attempts = float(R_TOTAL) * P * n * K
+    value = attempts / (ms * 1e-3)
+    pk, pk_kind = peaks()
+    per_launch_attempts = float(R) * P * n * K / launches
+    avg_launch_s = ms * 1e-3 / launches
+    achieved = B_ALG_HBM * per_launch_attempts / avg_launch_s / 1e9
+    sm_mhz = (clocks or {}).get("sm_mhz") or pk.get("sm_max_mhz", 1965.0)
+    nsm = torch.cuda.get_device_properties(local).multi_processor_count
+    smem_peak = 128.0 * nsm * sm_mhz * 1e6 / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": "attempts/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": config_dict(args),
+        "clocks": clocks,
+        "e2e": {"value": attempts / e2e_s, "unit": "attempts/s", "h2d_bytes_per_step": h2d / K,
+                "d2h_bytes_per_step": d2h / K, "seconds": e2e_s},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": "colour_sweep", "achieved": achieved, "peak": pk["hbm_gbs"],
+                     "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": None,
+                     "peak_source": pk_kind, "bytes_per_attempt": B_ALG_HBM,
+                     "note": "issue-bound kernel (~tens of instructions per attempt, no contraction); "
+                             "HBM fraction is low by construction, see DESIGN.md section 4"},
+        "roofline_smem": {"achieved": B_ALG_SMEM * value / world / 1e9, "peak": smem_peak, "unit": "GB/s",
+                          "frac": B_ALG_SMEM * value / world / 1e9 / smem_peak,
+                          "bytes_per_attempt": B_ALG_SMEM, "peak_source": "128 B/clk/SM x %d SMs x %.0f MHz" % (nsm, sm_mhz)},
+        "gather_ms": gather_ms,
+        "residual_energy_per_spin": {"mean_over_slices": float(en.mean() / n), "best_slice_mean": float(en.min(axis=1).mean() / n)},
+    }
+    # ---- CPU baseline on this box's host cores (bounded sample), rank 0, N=1 only
+    if world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        r_qa, w_qa, kind = cpu_rate(nbs, 3, "qa", cores)
+        r_par, w_par, _ = cpu_rate(nbs, 3, "qa_par", cores)
+        r_1, w_1, _ = cpu_rate(nbs, 3, "qa", 1)
+        line["cpu_baseline"] = {
+            "value": max(r_qa, r_par), "unit": "attempts/s", "cores": cores, "kind": kind,
+            "sample": "%d replicas (one per core) x 3 sweeps of the same 256x256 P=64 workload" % cores,
+            "qmc.QuantumAnneal": r_qa, "qmc.QuantumAnneal_parallel(nthreads=1)": r_par,
+            "qmc.QuantumAnneal_1core": r_1}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--order", default="natural", choices=["natural", "checkerboard"])
+    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

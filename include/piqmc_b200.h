@@ -17,7 +17,7 @@
  *
  * Spin / bit convention (piqmc/tools.pyx:20-26): bit 0 <-> spin +1, bit 1 <-> spin -1.
  *
- * Packed state ("words"): uint64 word[row][spin]; bit `lane` of a word is
+ * Packed state ("words"): uint64 word[spin][row] (row fastest); bit `lane` of a word is
  *   - quantum annealing: Trotter slice `lane` of replica `row`        (lanes = P <= 64)
  *   - simulated annealing: replica `row*64 + lane`                    (lanes = 64)
  */
@@ -76,6 +76,16 @@ int     piqmc_rand_restore_libc(const piqmc_rand_state *s);
  * zero couplings); it may be NULL when only the deterministic paths are used. */
 int piqmc_set_graph(piqmc_handle h, int nspins, int maxnb, const int32_t *idx, const double *J,
                     int ncolors, const int32_t *color);
+/* replace the colouring of the current graph (cheap: only the class member lists change) */
+int piqmc_set_colouring(piqmc_handle h, int ncolors, const int32_t *color);
+/* Level colouring of a sequential visiting order (host only, no device work):
+ * level[i] = 1 + max(level[j]) over coupled neighbours j visited before i (0 if none).  Updating
+ * the levels in ascending order, all spins of a level at once, gives exactly the result of the
+ * sequential sweep in that order -- this is how the colour kernels reproduce the reference's
+ * natural-order (piqmc/qmc.pyx:320) and permutation-order (piqmc/sa.pyx:100) sweeps.
+ * order[t] = spin visited at step t (NULL = natural order 0..N-1).  Returns the level count. */
+int piqmc_order_levels(int nspins, int maxnb, const int32_t *idx, const double *J,
+                       const int32_t *order, int32_t *level);
 
 /* ---- deterministic, reference-stream paths (bit-exact) --------------------------------
  * One replica per GPU thread, each replaying the reference's sequential algorithm with the
@@ -124,6 +134,7 @@ int piqmc_state_init_random(piqmc_handle h, uint64_t seed, uint32_t row0, int ti
 /* spins[(row*nspins + i)] +-1, copied to every lane (tile != 0), or
  * spins[(row*lanes + lane)*nspins + i] (tile == 0) */
 int piqmc_state_upload_spins(piqmc_handle h, const int8_t *spins, int tile);
+/* words[i*nrows + row], the device layout */
 int piqmc_state_upload_words(piqmc_handle h, const uint64_t *words);
 int piqmc_state_download_words(piqmc_handle h, uint64_t *words);
 /* device pointer of the packed state / of the last energy result (for NCCL gathers) */
@@ -134,12 +145,16 @@ void *piqmc_energy_devptr(piqmc_handle h);
  * per-spin ediff reset, J_perp recomputed per schedule step.  trotter = 0: neighbours slices-1
  * and 1 (reference, qmc.pyx:115-117); trotter = 1: periodic k-1,k+1 (requires even slices).
  * replica0: global id of row 0 (so results do not depend on how replicas are sharded).
- * Asynchronous on the handle's stream. */
+ * orders: NULL -> every sweep uses the graph's colouring; else orders[s*nspins + t] is the spin
+ * visited at step t of sweep s (s < nsched*mcsteps): each sweep is run through the level
+ * colouring of its own order and so equals the sequential sweep in that order.
+ * Asynchronous on the handle's stream when orders == NULL. */
 int piqmc_qa_colour(piqmc_handle h, const double *sched, int nsched, int mcsteps, float temp,
-                    uint64_t seed, uint32_t replica0, uint32_t sweep0, int trotter);
+                    uint64_t seed, uint32_t replica0, uint32_t sweep0, int trotter,
+                    const int32_t *orders);
 /* Classical SA sweeps over the resident state (lanes = 64 replicas per word, sa.Anneal rules). */
 int piqmc_sa_colour(piqmc_handle h, const double *sched, int nsched, int mcsteps,
-                    uint64_t seed, uint32_t row0, uint32_t sweep0);
+                    uint64_t seed, uint32_t row0, uint32_t sweep0, const int32_t *orders);
 /* kernel variant selection for piqmc_qa_colour / piqmc_sa_colour: 0 = auto, 1 = generic,
  * 2 = table-lookup fast path (falls back to generic when the graph does not qualify) */
 int piqmc_set_variant(piqmc_handle h, int variant);

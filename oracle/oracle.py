@@ -78,12 +78,12 @@ def lib():
         L.oracle_qa_colour.argtypes = [c_dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                        ctypes.c_int, ctypes.c_int, c_ip, c_fp, ctypes.c_int, c_ip,
                                        ctypes.c_int, c_bp, ctypes.c_uint64, ctypes.c_uint32,
-                                       ctypes.c_uint32, ctypes.c_int]
+                                       ctypes.c_uint32, ctypes.c_int, c_ip]
         L.oracle_sa_colour.restype = None
         L.oracle_sa_colour.argtypes = [c_dp, ctypes.c_int, ctypes.c_int,
                                        ctypes.c_int, ctypes.c_int, c_ip, c_fp, ctypes.c_int, c_ip,
                                        ctypes.c_int, c_bp, ctypes.c_uint64, ctypes.c_uint32,
-                                       ctypes.c_uint32]
+                                       ctypes.c_uint32, c_ip]
         L.oracle_energy_ell.restype = ctypes.c_double
         L.oracle_energy_ell.argtypes = [ctypes.c_int, ctypes.c_int, c_ip, c_fp, c_bp, ctypes.c_long]
         _lib = L
@@ -226,8 +226,18 @@ def colour_init_spins(seed, replica0, nreplicas, nspins):
     return out
 
 
-def qa_colour(sched, mcsteps, slices, temp, idx, J, color, spins, seed, replica0=0, sweep0=0, trotter=0):
-    """spins int8[R,N,P] in place."""
+def _orders(orders, nsweeps, n):
+    if orders is None:
+        return None, None
+    o = np.ascontiguousarray(orders, dtype=np.int32)
+    assert o.shape == (nsweeps, n)
+    return o, _p(o, c_ip)
+
+
+def qa_colour(sched, mcsteps, slices, temp, idx, J, color, spins, seed, replica0=0, sweep0=0, trotter=0,
+              orders=None):
+    """spins int8[R,N,P] in place.  orders int32[nsweeps,N]: sequential sweeps in those visiting
+    orders instead of colour classes."""
     sched = np.ascontiguousarray(sched, dtype=np.float64)
     idx = np.ascontiguousarray(idx, dtype=np.int32)
     J = np.ascontiguousarray(J, dtype=np.float32)
@@ -237,10 +247,11 @@ def qa_colour(sched, mcsteps, slices, temp, idx, J, color, spins, seed, replica0
     assert P == slices and idx.shape == J.shape == (N, idx.shape[1])
     lib().oracle_qa_colour(_p(sched, c_dp), sched.size, mcsteps, slices, ctypes.c_float(temp),
                            N, idx.shape[1], _p(idx, c_ip), _p(J, c_fp), int(color.max()) + 1,
-                           _p(color, c_ip), R, _p(spins, c_bp), seed, replica0, sweep0, trotter)
+                           _p(color, c_ip), R, _p(spins, c_bp), seed, replica0, sweep0, trotter,
+                           _orders(orders, sched.size * mcsteps, N)[1])
 
 
-def sa_colour(sched, mcsteps, idx, J, color, spins, seed, row0=0, sweep0=0):
+def sa_colour(sched, mcsteps, idx, J, color, spins, seed, row0=0, sweep0=0, orders=None):
     """spins int8[R,N] in place."""
     sched = np.ascontiguousarray(sched, dtype=np.float64)
     idx = np.ascontiguousarray(idx, dtype=np.int32)
@@ -250,7 +261,7 @@ def sa_colour(sched, mcsteps, idx, J, color, spins, seed, row0=0, sweep0=0):
     R, N = spins.shape
     lib().oracle_sa_colour(_p(sched, c_dp), sched.size, mcsteps, N, idx.shape[1], _p(idx, c_ip),
                            _p(J, c_fp), int(color.max()) + 1, _p(color, c_ip), R, _p(spins, c_bp),
-                           seed, row0, sweep0)
+                           seed, row0, sweep0, _orders(orders, sched.size * mcsteps, N)[1])
 
 
 def energy_ell(idx, J, s):

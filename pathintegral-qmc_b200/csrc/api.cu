@@ -77,6 +77,145 @@ int use(piqmc_ctx *c)
         if (rc__ != PIQMC_OK) return rc__;      \
     } while (0)
 
+
+// proper colouring: coupled spins (non-zero J, not self) never share a colour
+static int check_colouring(int nspins, int maxnb, const int32_t *idx, const double *J, int ncolors,
+                           const int32_t *color)
+{
+    PIQMC_REQUIRE(ncolors > 0, PIQMC_EINVAL, "ncolors must be positive");
+    for (int i = 0; i < nspins; i++) {
+        PIQMC_REQUIRE(color[i] >= 0 && color[i] < ncolors, PIQMC_EINVAL, "color[%d] out of range", i);
+        for (int n = 0; n < maxnb; n++) {
+            const int j = idx[(size_t)i * maxnb + n];
+            if (j != i && J[(size_t)i * maxnb + n] != 0.0)
+                PIQMC_REQUIRE(color[j] != color[i], PIQMC_EINVAL,
+                              "improper colouring: spins %d and %d are coupled and share colour %d", i, j,
+                              color[i]);
+        }
+    }
+    return PIQMC_OK;
+}
+
+// bucket spins by colour (ascending spin index inside a class); offsets -> off[ncolors+1]
+static void bucket_members(int nspins, int ncolors, const int32_t *color, std::vector<int> &off,
+                           int32_t *members)
+{
+    off.assign(ncolors + 1, 0);
+    for (int i = 0; i < nspins; i++) off[color[i] + 1]++;
+    for (int c = 0; c < ncolors; c++) off[c + 1] += off[c];
+    std::vector<int> fill(off.begin(), off.end() - 1);
+    for (int i = 0; i < nspins; i++) members[fill[color[i]]++] = i;
+}
+
+static int apply_colouring(piqmc_ctx *h, int ncolors, const int32_t *color, bool validate)
+{
+    if (validate) {
+        PIQMC_REQUIRE(ncolors > 0 && color, PIQMC_EINVAL, "bad colouring");
+        for (int i = 0; i < h->nspins; i++) {
+            PIQMC_REQUIRE(color[i] >= 0 && color[i] < ncolors, PIQMC_EINVAL, "color[%d] out of range", i);
+            for (int n = 0; n < h->maxnb; n++) {
+                const size_t e = (size_t)i * h->maxnb + n;
+                if (h->h_live[e])
+                    PIQMC_REQUIRE(color[h->h_idx[e]] != color[i], PIQMC_EINVAL,
+                                  "improper colouring: spins %d and %d are coupled and share colour %d", i,
+                                  h->h_idx[e], color[i]);
+            }
+        }
+    }
+    std::vector<int32_t> members(h->nspins);
+    bucket_members(h->nspins, ncolors, color, h->color_off, members.data());
+    PIQMC_CUDA(cudaStreamSynchronize(h->stream));     // the old lists may still be in use
+    PIQMC_CUDA(cudaMemcpy(h->d_members, members.data(), (size_t)h->nspins * sizeof(int32_t),
+                          cudaMemcpyHostToDevice));
+    h->ncolors = ncolors;
+    return PIQMC_OK;
+}
+
+// level[i] = 1 + max(level of coupled neighbours visited earlier); returns the number of levels
+static int order_levels(int nspins, int maxnb, const int32_t *idx, const uint8_t *live,
+                        const int32_t *order, int32_t *level)
+{
+    for (int i = 0; i < nspins; i++) level[i] = -1;
+    int nlev = 0;
+    for (int t = 0; t < nspins; t++) {
+        const int i = order ? order[t] : t;
+        int m = -1;
+        for (int n = 0; n < maxnb; n++) {
+            const size_t e = (size_t)i * maxnb + n;
+            if (live[e]) {
+                const int l = level[idx[e]];
+                if (l > m) m = l;
+            }
+        }
+        level[i] = m + 1;
+        if (m + 2 > nlev) nlev = m + 2;
+    }
+    return nlev;
+}
+
+static int check_orders(int nspins, size_t nsweeps, const int32_t *orders)
+{
+    std::vector<uint8_t> seen(nspins);
+    for (size_t s = 0; s < nsweeps; s++) {
+        std::fill(seen.begin(), seen.end(), 0);
+        for (int t = 0; t < nspins; t++) {
+            const int i = orders[s * nspins + t];
+            PIQMC_REQUIRE(i >= 0 && i < nspins && !seen[i], PIQMC_EINVAL,
+                          "orders[%zu] is not a permutation of 0..%d", s, nspins - 1);
+            seen[i] = 1;
+        }
+    }
+    return PIQMC_OK;
+}
+
+// Sweeps driver shared by QA and SA.  value[f] is jp2 (QA) or unused; invT[f] per schedule step.
+static int run_colour_sweeps(piqmc_ctx *h, int qa, int trotter, int nsched, int mcsteps,
+                             const std::vector<float> &jp2, const std::vector<float> &invT, uint64_t seed,
+                             uint32_t row0, uint32_t sweep0, const int32_t *orders)
+{
+    const int N = h->nspins;
+    uint32_t sweep = sweep0;
+    if (!orders) {
+        PIQMC_REQUIRE(h->ncolors > 0, PIQMC_ENOGRAPH, "graph has no colouring");
+        for (int f = 0; f < nsched; f++)
+            for (int s = 0; s < mcsteps; s++, sweep++)
+                for (int c = 0; c < h->ncolors; c++)
+                    TRY(launch_colour_sweep(h, qa, trotter, h->d_members + h->color_off[c],
+                                            h->color_off[c + 1] - h->color_off[c], jp2[f], invT[f], seed, row0,
+                                            sweep));
+        return PIQMC_OK;
+    }
+    // per-sweep visiting orders: level-colour each sweep on the host, ship the member lists in
+    // chunks (bounded device memory), launch level by level
+    const size_t nsweeps = (size_t)nsched * mcsteps;
+    TRY(check_orders(N, nsweeps, orders));
+    const size_t chunk = std::max<size_t>(1, std::min<size_t>(nsweeps, (size_t)(64u << 20) / ((size_t)N * 4)));
+    DevBuf<int32_t> d_mem;
+    PIQMC_CUDA(d_mem.alloc(chunk * N));
+    std::vector<int32_t> members(chunk * N), level(N);
+    std::vector<std::vector<int>> offs(chunk);
+    for (size_t base = 0; base < nsweeps; base += chunk) {
+        const size_t m = std::min(chunk, nsweeps - base);
+        for (size_t s = 0; s < m; s++) {
+            const int nlev = order_levels(N, h->maxnb, h->h_idx.data(), h->h_live.data(),
+                                          orders + (base + s) * N, level.data());
+            bucket_members(N, nlev, level.data(), offs[s], members.data() + s * N);
+        }
+        PIQMC_CUDA(cudaStreamSynchronize(h->stream));     // previous chunk's lists no longer in use
+        PIQMC_CUDA(cudaMemcpyAsync(d_mem.p, members.data(), m * N * sizeof(int32_t), cudaMemcpyHostToDevice,
+                                   h->stream));
+        for (size_t s = 0; s < m; s++, sweep++) {
+            const int f = (int)((base + s) / mcsteps);
+            const std::vector<int> &off = offs[s];
+            for (size_t c = 0; c + 1 < off.size(); c++)
+                TRY(launch_colour_sweep(h, qa, trotter, d_mem.p + s * N + off[c], off[c + 1] - off[c], jp2[f],
+                                        invT[f], seed, row0, sweep));
+        }
+        PIQMC_CUDA(cudaStreamSynchronize(h->stream));     // d_mem / members are reused or freed next
+    }
+    return PIQMC_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -221,19 +360,7 @@ int piqmc_set_graph(piqmc_handle h, int nspins, int maxnb, const int32_t *idx, c
     for (size_t e = 0; e < ne; e++)
         PIQMC_REQUIRE(idx[e] >= 0 && idx[e] < nspins, PIQMC_EINVAL,
                       "neighbour index %d out of range at entry %zu", idx[e], e);
-    if (color) {
-        PIQMC_REQUIRE(ncolors > 0, PIQMC_EINVAL, "ncolors must be positive");
-        for (int i = 0; i < nspins; i++) {
-            PIQMC_REQUIRE(color[i] >= 0 && color[i] < ncolors, PIQMC_EINVAL, "color[%d] out of range", i);
-            for (int n = 0; n < maxnb; n++) {
-                const int j = idx[(size_t)i * maxnb + n];
-                if (j != i && J[(size_t)i * maxnb + n] != 0.0)
-                    PIQMC_REQUIRE(color[j] != color[i], PIQMC_EINVAL,
-                                  "improper colouring: spins %d and %d are coupled and share colour %d",
-                                  i, j, color[i]);
-            }
-        }
-    }
+    if (color) TRY(check_colouring(nspins, maxnb, idx, J, ncolors, color));
     PIQMC_CUDA(cudaStreamSynchronize(h->stream));
     free_graph(h);
 
@@ -258,22 +385,42 @@ int piqmc_set_graph(piqmc_handle h, int nspins, int maxnb, const int32_t *idx, c
     PIQMC_CUDA(cudaMemcpy(h->d_J32_t, j32t.data(), ne * sizeof(float), cudaMemcpyHostToDevice));
     h->nspins = nspins;
     h->maxnb = maxnb;
-    if (color) {
-        std::vector<int32_t> members(nspins);
-        h->color_off.assign(ncolors + 1, 0);
-        for (int i = 0; i < nspins; i++) h->color_off[color[i] + 1]++;
-        for (int c = 0; c < ncolors; c++) h->color_off[c + 1] += h->color_off[c];
-        std::vector<int> fill(h->color_off.begin(), h->color_off.end() - 1);
-        for (int i = 0; i < nspins; i++) members[fill[color[i]]++] = i;   // ascending within a class
-        PIQMC_CUDA(cudaMalloc(&h->d_members, (size_t)nspins * sizeof(int32_t)));
-        PIQMC_CUDA(cudaMemcpy(h->d_members, members.data(), (size_t)nspins * sizeof(int32_t),
-                              cudaMemcpyHostToDevice));
-        h->ncolors = ncolors;
-        TRY(build_lut(h));
-    }
+    h->h_idx.assign(idx, idx + ne);
+    h->h_live.resize(ne);
+    for (int i = 0; i < nspins; i++)
+        for (int n = 0; n < maxnb; n++) {
+            const size_t e = (size_t)i * maxnb + n;
+            h->h_live[e] = (idx[e] != i && J[e] != 0.0) ? 1 : 0;
+        }
+    PIQMC_CUDA(cudaMalloc(&h->d_members, (size_t)nspins * sizeof(int32_t)));
+    if (color) TRY(apply_colouring(h, ncolors, color, false));
+    TRY(build_lut(h));
     // a new graph invalidates any resident state
     free_state(h);
     return PIQMC_OK;
+}
+
+int piqmc_set_colouring(piqmc_handle h, int ncolors, const int32_t *color)
+{
+    USE(h);
+    PIQMC_REQUIRE(h->nspins > 0, PIQMC_ENOGRAPH, "piqmc_set_graph has not been called");
+    return apply_colouring(h, ncolors, color, true);
+}
+
+int piqmc_order_levels(int nspins, int maxnb, const int32_t *idx, const double *J, const int32_t *order,
+                       int32_t *level)
+{
+    PIQMC_REQUIRE(nspins > 0 && maxnb > 0 && idx && J && level, PIQMC_EINVAL, "bad arguments");
+    const size_t ne = (size_t)nspins * maxnb;
+    std::vector<uint8_t> live(ne);
+    for (int i = 0; i < nspins; i++)
+        for (int n = 0; n < maxnb; n++) {
+            const size_t e = (size_t)i * maxnb + n;
+            PIQMC_REQUIRE(idx[e] >= 0 && idx[e] < nspins, PIQMC_EINVAL, "neighbour index out of range");
+            live[e] = (idx[e] != i && J[e] != 0.0) ? 1 : 0;
+        }
+    if (order) TRY(check_orders(nspins, 1, order));
+    return order_levels(nspins, maxnb, idx, live.data(), order, level);
 }
 
 // ---- deterministic paths ---------------------------------------------------------------------
@@ -488,41 +635,28 @@ int piqmc_set_variant(piqmc_handle h, int variant)
 
 // ---- production sweeps -----------------------------------------------------------------------
 int piqmc_qa_colour(piqmc_handle h, const double *sched, int nsched, int mcsteps, float temp,
-                    uint64_t seed, uint32_t replica0, uint32_t sweep0, int trotter)
+                    uint64_t seed, uint32_t replica0, uint32_t sweep0, int trotter, const int32_t *orders)
 {
     USE(h);
     PIQMC_REQUIRE(h->d_words, PIQMC_ENOSTATE, "no packed state (call piqmc_state_alloc)");
-    PIQMC_REQUIRE(h->ncolors > 0, PIQMC_ENOGRAPH, "graph has no colouring");
     PIQMC_REQUIRE(sched && nsched >= 0 && mcsteps >= 0, PIQMC_EINVAL, "bad schedule");
     PIQMC_REQUIRE(trotter == 0 || trotter == 1, PIQMC_EINVAL, "trotter must be 0 or 1");
     PIQMC_REQUIRE(h->lanes >= 2, PIQMC_EINVAL, "slices must be >= 2");
     PIQMC_REQUIRE((float)h->lanes * temp != 0.0f && temp != 0.0f, PIQMC_EZERODIV, "float division");
-    const float invT = 1.0f / temp;
-    uint32_t sweep = sweep0;
-    for (int f = 0; f < nsched; f++) {
-        const float jp2 = 2.0f * piqmc_jperp(sched[f], h->lanes, temp);
-        for (int s = 0; s < mcsteps; s++, sweep++)
-            for (int c = 0; c < h->ncolors; c++)
-                TRY(launch_colour_sweep(h, 1, trotter, c, jp2, invT, seed, replica0, sweep));
-    }
-    return PIQMC_OK;
+    std::vector<float> jp2(std::max(nsched, 1)), invT(std::max(nsched, 1), 1.0f / temp);
+    for (int f = 0; f < nsched; f++) jp2[f] = 2.0f * piqmc_jperp(sched[f], h->lanes, temp);
+    return run_colour_sweeps(h, 1, trotter, nsched, mcsteps, jp2, invT, seed, replica0, sweep0, orders);
 }
 
 int piqmc_sa_colour(piqmc_handle h, const double *sched, int nsched, int mcsteps, uint64_t seed,
-                    uint32_t row0, uint32_t sweep0)
+                    uint32_t row0, uint32_t sweep0, const int32_t *orders)
 {
     USE(h);
     PIQMC_REQUIRE(h->d_words, PIQMC_ENOSTATE, "no packed state (call piqmc_state_alloc)");
-    PIQMC_REQUIRE(h->ncolors > 0, PIQMC_ENOGRAPH, "graph has no colouring");
     PIQMC_REQUIRE(sched && nsched >= 0 && mcsteps >= 0, PIQMC_EINVAL, "bad schedule");
-    uint32_t sweep = sweep0;
-    for (int t = 0; t < nsched; t++) {
-        const float invT = 1.0f / (float)sched[t];
-        for (int s = 0; s < mcsteps; s++, sweep++)
-            for (int c = 0; c < h->ncolors; c++)
-                TRY(launch_colour_sweep(h, 0, 0, c, 0.0f, invT, seed, row0, sweep));
-    }
-    return PIQMC_OK;
+    std::vector<float> jp2(std::max(nsched, 1), 0.0f), invT(std::max(nsched, 1));
+    for (int t = 0; t < nsched; t++) invT[t] = 1.0f / (float)sched[t];
+    return run_colour_sweeps(h, 0, 0, nsched, mcsteps, jp2, invT, seed, row0, sweep0, orders);
 }
 
 // ---- energies --------------------------------------------------------------------------------

@@ -1,9 +1,12 @@
 // colour_kernels.cu -- production colour-parallel Metropolis sweeps on bit-packed state.
 //
-// State: uint64 word[row][spin]; bit `lane` = Trotter slice (QA) or replica-in-group (SA).
-// One thread owns one (row, spin) word of the colour class being updated and walks its lanes;
-// all neighbour words belong to other colour classes and are constant during the launch, so
-// the launch is race-free for any proper colouring.  Semantics: oracle/piqmc_oracle.c part 3
+// State: uint64 word[spin][row] (row fastest: consecutive threads = consecutive rows, so every
+// access is coalesced whatever the shape of the colour class); bit `lane` = Trotter slice (QA)
+// or replica-in-group (SA).  One thread owns one (spin, row) word of the class being updated
+// and walks its lanes; all neighbour words belong to other classes and are constant during the
+// launch, so the launch is race-free for any proper colouring.  Classes are processed in
+// ascending order; when they are the dependency levels of a sequential visiting order
+// (tools.ColourGraph(order=...)) the sweep equals the sequential sweep in that order.  Semantics: oracle/piqmc_oracle.c part 3
 // (oracle_qa_colour / oracle_sa_colour), reproduced bit-exactly.
 //
 // Bandwidth: per launch each word of the class is read and written once and its neighbour
@@ -37,16 +40,16 @@ __device__ __forceinline__ bool metropolis(float e, float invT, uint32_t u)
 // ------------------------------------------------------------------------------------------
 template <int NL, bool QA, int TROTTER>
 __global__ void __launch_bounds__(128) colour_sweep_generic(
-    uint64_t *__restrict__ words, int nspins, int maxnb, const int32_t *__restrict__ idx_t,
+    uint64_t *__restrict__ words, int nspins, int nrows, int maxnb, const int32_t *__restrict__ idx_t,
     const float *__restrict__ J_t, const int32_t *__restrict__ members, int nmembers, int lanes,
     float jp2, float invT, uint32_t k0, uint32_t k1, uint32_t row0, uint32_t sweep)
 {
-    const int m = blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= nmembers) return;
-    const int row = blockIdx.y;
-    const int i = members[m];
-    uint64_t *wrow = words + (size_t)row * nspins;
-    uint64_t w = wrow[i];
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (size_t)nmembers * nrows) return;
+    const int row = (int)(tid % nrows);
+    const int i = members[tid / nrows];
+    uint64_t *wrow = words + row;                     // word of spin s at wrow[s*nrows]
+    uint64_t w = wrow[(size_t)i * nrows];
 
     float e[NL];
 #pragma unroll
@@ -54,7 +57,7 @@ __global__ void __launch_bounds__(128) colour_sweep_generic(
     for (int n = 0; n < maxnb; n++) {
         const int j = idx_t[(size_t)n * nspins + i];
         const float negJ2 = -2.0f * J_t[(size_t)n * nspins + i];
-        const uint64_t x = (j == i) ? w : (w ^ wrow[j]);
+        const uint64_t x = (j == i) ? w : (w ^ wrow[(size_t)j * nrows]);
 #pragma unroll
         for (int k = 0; k < NL; k++)
             e[k] = __fadd_rn(e[k], flip_sign(negJ2, (uint32_t)(x >> k) & 1u));
@@ -88,16 +91,18 @@ __global__ void __launch_bounds__(128) colour_sweep_generic(
                             }
                             const uint32_t bl = (uint32_t)(w >> kl) & 1u;
                             const uint32_t br = (uint32_t)(w >> kr) & 1u;
-                            ee = __fadd_rn(ee, flip_sign(njp2, own ^ bl));
-                            ee = __fadd_rn(ee, flip_sign(njp2, own ^ br));
+                            // exact sum of the two Trotter terms (0 or +-2*jp2), one rounding
+                            const float tsum = __fadd_rn(flip_sign(njp2, own ^ bl), flip_sign(njp2, own ^ br));
+                            ee = __fadd_rn(ee, tsum);
                         }
+                        ee = __fadd_rn(ee, 0.0f);          // canonical zero (-0 -> +0)
                         if (metropolis<QA>(ee, invT, rr[q])) w ^= (1ull << k);
                     }
                 }
             }
         }
     }
-    wrow[i] = w;
+    wrow[(size_t)i * nrows] = w;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -108,7 +113,7 @@ __global__ void state_init_kernel(uint64_t *words, int nspins, int nrows, int la
 {
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= (size_t)nrows * nspins) return;
-    const uint32_t row = (uint32_t)(tid / nspins), i = (uint32_t)(tid % nspins);
+    const uint32_t row = (uint32_t)(tid % nrows), i = (uint32_t)(tid / nrows);
     uint64_t w = 0;
     if (tile) {
         const u32x4 r = philox4x32_10(i, PIQMC_STREAM_INIT << 16, 0u, row0 + row, k0, k1);
@@ -127,7 +132,7 @@ __global__ void pack_spins_kernel(uint64_t *words, const int8_t *spins, int nspi
 {
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= (size_t)nrows * nspins) return;
-    const size_t row = tid / nspins, i = tid % nspins;
+    const size_t row = tid % nrows, i = tid / nrows;
     uint64_t w = 0;
     if (tile) {
         if (spins[row * nspins + i] < 0) w = (lanes == 64) ? ~0ull : ((1ull << lanes) - 1ull);
@@ -160,17 +165,15 @@ int launch_pack_spins(piqmc_ctx *c, const int8_t *d_spins, int tile)
     return PIQMC_OK;
 }
 
-int launch_colour_sweep_lut(piqmc_ctx *c, int qa, int trotter, int color, float jp2, float invT,
-                            uint64_t seed, uint32_t row0, uint32_t sweep);
-
 template <int NL>
 static int launch_generic(piqmc_ctx *c, int qa, int trotter, const int32_t *members, int nmem,
                           float jp2, float invT, uint64_t seed, uint32_t row0, uint32_t sweep)
 {
-    dim3 block(128), grid((nmem + 127) / 128, c->nrows);
+    const size_t total = (size_t)nmem * c->nrows;
+    dim3 block(128), grid((unsigned)((total + 127) / 128));
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-#define ARGS c->d_words, c->nspins, c->maxnb, c->d_idx_t, c->d_J32_t, members, nmem, c->lanes, jp2, \
-             invT, k0, k1, row0, sweep
+#define ARGS c->d_words, c->nspins, c->nrows, c->maxnb, c->d_idx_t, c->d_J32_t, members, nmem, c->lanes, \
+             jp2, invT, k0, k1, row0, sweep
     if (!qa)
         colour_sweep_generic<NL, false, 0><<<grid, block, 0, c->stream>>>(ARGS);
     else if (trotter == 1)
@@ -183,13 +186,10 @@ static int launch_generic(piqmc_ctx *c, int qa, int trotter, const int32_t *memb
     return PIQMC_OK;
 }
 
-int launch_colour_sweep(piqmc_ctx *c, int qa, int trotter, int color, float jp2, float invT,
-                        uint64_t seed, uint32_t row0, uint32_t sweep)
+int launch_colour_sweep(piqmc_ctx *c, int qa, int trotter, const int32_t *members, int nmem, float jp2,
+                        float invT, uint64_t seed, uint32_t row0, uint32_t sweep)
 {
-    const int off = c->color_off[color];
-    const int nmem = c->color_off[color + 1] - off;
     if (nmem == 0) return PIQMC_OK;
-    const int32_t *members = c->d_members + off;
     if (c->lanes <= 8) return launch_generic<8>(c, qa, trotter, members, nmem, jp2, invT, seed, row0, sweep);
     if (c->lanes <= 16) return launch_generic<16>(c, qa, trotter, members, nmem, jp2, invT, seed, row0, sweep);
     if (c->lanes <= 32) return launch_generic<32>(c, qa, trotter, members, nmem, jp2, invT, seed, row0, sweep);

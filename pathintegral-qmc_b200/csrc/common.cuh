@@ -46,14 +46,16 @@ struct piqmc_ctx {
     double *d_J64 = nullptr;        // [N][maxnb]  (energy reduction)
     int32_t *d_idx_t = nullptr;     // [maxnb][N]  transposed, coalesced over spins (colour kernels)
     float *d_J32_t = nullptr;       // [maxnb][N]
-    int32_t *d_members = nullptr;   // spins sorted by colour
+    int32_t *d_members = nullptr;   // spins sorted by colour (static colouring)
     std::vector<int> color_off;     // ncolors+1 offsets into d_members
+    std::vector<int32_t> h_idx;     // host copies for level colourings of per-sweep orders
+    std::vector<uint8_t> h_live;    // J != 0 && idx != self
     bool lut_ok = false;            // graph qualifies for the table-lookup fast path
     float *d_lut = nullptr;         // [N][16] in-slice partial sums per neighbour pattern (maxnb<=4)
 
     // packed state
     int nrows = 0, lanes = 0;
-    uint64_t *d_words = nullptr;    // [nrows][N]
+    uint64_t *d_words = nullptr;    // [N][nrows]  (row fastest)
     double *d_energy = nullptr;     // [nrows][lanes]
     double *d_epart = nullptr;      // scratch for the energy reduction
     size_t epart_elems = 0;
@@ -122,9 +124,9 @@ int launch_sa_multispin_det(piqmc_ctx *c, const float *d_temps, int nsched, int 
 
 int launch_state_init(piqmc_ctx *c, uint64_t seed, uint32_t row0, int tile);
 int launch_pack_spins(piqmc_ctx *c, const int8_t *d_spins, int tile);
-// one colour class of one sweep; qa != 0: QA rules with Trotter terms (jp2 = 2*jperp)
-int launch_colour_sweep(piqmc_ctx *c, int qa, int trotter, int color, float jp2, float invT,
-                        uint64_t seed, uint32_t row0, uint32_t sweep);
+// one colour class (device list `members`) of one sweep; qa != 0: QA rules (jp2 = 2*jperp)
+int launch_colour_sweep(piqmc_ctx *c, int qa, int trotter, const int32_t *members, int nmem, float jp2,
+                        float invT, uint64_t seed, uint32_t row0, uint32_t sweep);
 int launch_energy(piqmc_ctx *c);
 int launch_energy_coo(piqmc_ctx *c, int nspins, int nnz, const int32_t *d_row, const int32_t *d_col,
                       const double *d_val, int nconfs, const int8_t *d_spins, double *d_out);

@@ -15,21 +15,21 @@ constexpr int EN_CHUNKS = 4;   // threadIdx.y sub-chunks per block
 // spins i = (bx*EN_CHUNKS + y), stepping by gridDim.x*EN_CHUNKS.  All 64 lanes of a warp pair
 // read the same words (broadcast), each extracting its own bit.
 __global__ void __launch_bounds__(64 * EN_CHUNKS) energy_partial_kernel(
-    const uint64_t *__restrict__ words, int nspins, int maxnb, const int32_t *__restrict__ idx,
-    const double *__restrict__ J, int lanes, double *__restrict__ part)
+    const uint64_t *__restrict__ words, int nspins, int nrows, int maxnb,
+    const int32_t *__restrict__ idx, const double *__restrict__ J, int lanes, double *__restrict__ part)
 {
     const int lane = threadIdx.x, y = threadIdx.y, row = blockIdx.y;
-    const uint64_t *wrow = words + (size_t)row * nspins;
+    const uint64_t *wrow = words + row;               // word of spin s at wrow[s*nrows]
     double eq = 0.0, el = 0.0;
     for (int i = blockIdx.x * EN_CHUNKS + y; i < nspins; i += gridDim.x * EN_CHUNKS) {
-        const uint64_t w = wrow[i];
+        const uint64_t w = wrow[(size_t)i * nrows];
         for (int n = 0; n < maxnb; n++) {
             const int j = idx[(size_t)i * maxnb + n];
             const double jv = J[(size_t)i * maxnb + n];
             if (j == i) {
                 el += ((w >> lane) & 1) ? -jv : jv;
             } else {
-                const uint64_t x = w ^ wrow[j];
+                const uint64_t x = w ^ wrow[(size_t)j * nrows];
                 eq += ((x >> lane) & 1) ? -jv : jv;
             }
         }
@@ -103,8 +103,8 @@ int launch_energy(piqmc_ctx *c)
         c->epart_elems = need;
     }
     dim3 block(64, EN_CHUNKS), grid(nbx, c->nrows);
-    energy_partial_kernel<<<grid, block, 0, c->stream>>>(c->d_words, c->nspins, c->maxnb, c->d_idx,
-                                                        c->d_J64, c->lanes, c->d_epart);
+    energy_partial_kernel<<<grid, block, 0, c->stream>>>(c->d_words, c->nspins, c->nrows, c->maxnb,
+                                                        c->d_idx, c->d_J64, c->lanes, c->d_epart);
     c->launches++;
     PIQMC_CUDA(cudaGetLastError());
     const int n = c->nrows * c->lanes;

@@ -43,6 +43,8 @@ SIGNATURES = {
     "piqmc_rand_capture_libc": (c_int, [P(RandState)]),
     "piqmc_rand_restore_libc": (c_int, [P(RandState)]),
     "piqmc_set_graph": (c_int, [c_void, c_int, c_int, c_void, c_void, c_int, c_void]),
+    "piqmc_set_colouring": (c_int, [c_void, c_int, c_void]),
+    "piqmc_order_levels": (c_int, [c_int, c_int, c_void, c_void, c_void, c_void]),
     "piqmc_qa_det": (c_int, [c_void, c_void, c_int, c_int, c_int, c_f, c_int, c_void, c_void, c_void,
                              c_void, c_u64, c_void]),
     "piqmc_sa_det": (c_int, [c_void, c_void, c_int, c_int, c_int, c_void, c_void, c_void, c_void,
@@ -56,8 +58,8 @@ SIGNATURES = {
     "piqmc_state_download_words": (c_int, [c_void, c_void]),
     "piqmc_state_devptr": (c_void, [c_void]),
     "piqmc_energy_devptr": (c_void, [c_void]),
-    "piqmc_qa_colour": (c_int, [c_void, c_void, c_int, c_int, c_f, c_u64, c_u32, c_u32, c_int]),
-    "piqmc_sa_colour": (c_int, [c_void, c_void, c_int, c_int, c_u64, c_u32, c_u32]),
+    "piqmc_qa_colour": (c_int, [c_void, c_void, c_int, c_int, c_f, c_u64, c_u32, c_u32, c_int, c_void]),
+    "piqmc_sa_colour": (c_int, [c_void, c_void, c_int, c_int, c_u64, c_u32, c_u32, c_void]),
     "piqmc_set_variant": (c_int, [c_void, c_int]),
     "piqmc_energy": (c_int, [c_void, c_void]),
     "piqmc_energy_coo": (c_int, [c_void, c_int, c_int, c_void, c_void, c_void, c_int, c_void, c_void]),

@@ -190,16 +190,23 @@ class Device:
         check(lib.piqmc_state_upload_spins(self._h, _ptr(spins), 1 if tile else 0))
 
     def state_upload_words(self, words):
-        words = np.ascontiguousarray(words, dtype=np.uint64)
+        """words uint64[nrows, nspins] (logical shape; stored spin-major on the device)."""
+        words = np.asarray(words, dtype=np.uint64)
         if words.shape != (self.nrows, self.nspins):
             raise ValueError("words must have shape (nrows, nspins)")
-        check(lib.piqmc_state_upload_words(self._h, _ptr(words)))
+        dev = np.ascontiguousarray(words.T)
+        check(lib.piqmc_state_upload_words(self._h, _ptr(dev)))
 
     def state_download_words(self, out=None):
+        """uint64 words of logical shape (nrows, nspins).  The device layout is word[spin][row], so
+        the result is the transposed VIEW of a C-contiguous (nspins, nrows) buffer (no host copy);
+        pass `out` (C-contiguous uint64[nspins, nrows], e.g. pinned) to reuse a buffer."""
         if out is None:
-            out = np.empty((self.nrows, self.nspins), dtype=np.uint64)
+            out = np.empty((self.nspins, self.nrows), dtype=np.uint64)
+        elif out.dtype != np.uint64 or not out.flags.c_contiguous or out.shape != (self.nspins, self.nrows):
+            raise ValueError("out must be C-contiguous uint64[nspins, nrows]")
         check(lib.piqmc_state_download_words(self._h, _ptr(out)))
-        return out
+        return out.T
 
     def state_download_spins(self):
         """int8[nrows, lanes, N] of +-1 (host-side unpack of the packed words)."""
@@ -209,22 +216,43 @@ class Device:
         return (1 - 2 * bits.astype(np.int8)).astype(np.int8)
 
     def state_device_array(self):
-        return DeviceArray(lib.piqmc_state_devptr(self._h), (self.nrows, self.nspins), "<u8", self)
+        """Device view of the packed state in its native (nspins, nrows) layout."""
+        return DeviceArray(lib.piqmc_state_devptr(self._h), (self.nspins, self.nrows), "<u8", self)
 
     def energy_device_array(self):
         return DeviceArray(lib.piqmc_energy_devptr(self._h), (self.nrows, self.lanes), "<f8", self)
 
     # ------------------------------------------------------------------ production sweeps
-    def qa_colour(self, sched, mcsteps, temp, seed, replica0=0, sweep0=0, trotter=0):
-        """Asynchronous: returns once the launches are queued on the Device's stream."""
-        sched = np.ascontiguousarray(sched, dtype=np.float64)
-        check(lib.piqmc_qa_colour(self._h, _ptr(sched), sched.size, int(mcsteps), ctypes.c_float(temp),
-                                  int(seed), int(replica0), int(sweep0), int(trotter)))
+    def _orders(self, orders, nsweeps):
+        if orders is None:
+            return None
+        o = np.ascontiguousarray(orders, dtype=np.int32)
+        if o.shape != (nsweeps, self.nspins):
+            raise ValueError("orders must have shape (nsweeps, nspins) = (%d, %d)" % (nsweeps, self.nspins))
+        return o
 
-    def sa_colour(self, sched, mcsteps, seed, row0=0, sweep0=0):
+    def qa_colour(self, sched, mcsteps, temp, seed, replica0=0, sweep0=0, trotter=0, orders=None):
+        """QA sweeps over the resident state.  orders=None: the graph's colouring, asynchronous
+        (returns once the launches are queued).  orders int32[nsweeps, N]: sweep s is the
+        sequential sweep visiting spins in orders[s] (run through its level colouring)."""
         sched = np.ascontiguousarray(sched, dtype=np.float64)
+        o = self._orders(orders, sched.size * int(mcsteps))
+        check(lib.piqmc_qa_colour(self._h, _ptr(sched), sched.size, int(mcsteps), ctypes.c_float(temp),
+                                  int(seed), int(replica0), int(sweep0), int(trotter), _ptr(o)))
+
+    def sa_colour(self, sched, mcsteps, seed, row0=0, sweep0=0, orders=None):
+        sched = np.ascontiguousarray(sched, dtype=np.float64)
+        o = self._orders(orders, sched.size * int(mcsteps))
         check(lib.piqmc_sa_colour(self._h, _ptr(sched), sched.size, int(mcsteps), int(seed), int(row0),
-                                  int(sweep0)))
+                                  int(sweep0), _ptr(o)))
+
+    def set_colouring(self, color):
+        col = np.ascontiguousarray(color, dtype=np.int32)
+        if col.shape != (self.nspins,):
+            raise ValueError("color must have one entry per spin")
+        check(lib.piqmc_set_colouring(self._h, int(col.max()) + 1, _ptr(col)))
+        self.ncolors = int(col.max()) + 1
+        self._graph_key = None
 
     # ------------------------------------------------------------------ energies
     def energy(self, download=True):
@@ -258,6 +286,17 @@ def default_device(index=0):
     if d is None:
         d = _default[index] = Device(index)
     return d
+
+
+def order_levels(nbs, order=None):
+    """Level colouring of a sequential visiting order (piqmc_order_levels): int32[N]."""
+    idx, J = split_nbs(nbs)
+    o = None if order is None else np.ascontiguousarray(order, dtype=np.int32)
+    level = np.empty(idx.shape[0], dtype=np.int32)
+    rc = lib.piqmc_order_levels(idx.shape[0], idx.shape[1], _ptr(idx), _ptr(J), _ptr(o), _ptr(level))
+    if rc < 0:
+        check(rc)
+    return level
 
 
 def device_count():

@@ -17,7 +17,7 @@ import numpy as np
 from . import device as _dev
 from . import tools as _tools
 from ._lib import RandState, lib
-from .sa import _draw_perms, _f64, _spins_i8
+from .sa import _draw_perms, _f64, _resolve_order, _spins_i8
 
 __all__ = ["QuantumAnneal", "QuantumAnneal_parallel", "QuantumAnnealBatch", "QuantumAnnealReplicas",
            "JPerp"]
@@ -100,12 +100,22 @@ def QuantumAnneal_parallel(sched, mcsteps, slices, temp, nspins, confs, nbs, nth
     return None
 
 
-def QuantumAnnealReplicas(sched, mcsteps, slices, temp, nspins, spins0, nbs, seed, color=None,
-                          replica0=0, trotter="reference", device=None, energies=True, tile=True,
-                          nreplicas=None, download=True):
+def QuantumAnnealReplicas(sched, mcsteps, slices, temp, nspins, spins0, nbs, seed, order="natural",
+                          color=None, replica0=0, trotter="reference", device=None, energies=True,
+                          tile=True, nreplicas=None, download=True):
     """Production PIQMC: R replicas x `slices` Trotter slices x nspins, one uint64 word per
     (replica, spin) holding all slices, colour-class Metropolis sweeps with Philox4x32-10 keyed by
     (seed; spin, slice, sweep, replica0 + r), J_perp recomputed per schedule step.
+
+    order: the sequential sweep each colour-class sweep is equivalent to --
+        "natural"      spins 0..N-1 in every slice: the order of the reference's per-spin-reset
+                       variant qmc.QuantumAnneal_parallel (qmc.pyx:320), whose residual-energy
+                       statistics this mode reproduces;
+        "permutation"  a fresh random permutation per sweep (qmc.pyx:100,136), from RandomState(seed);
+        "checkerboard" fewest classes (fastest; at T << J its quench statistics differ measurably
+                       from the natural-order sweep, see DESIGN.md);
+        int32[N] / int32[nsweeps,N]  explicit visiting order(s).
+    color: explicit colour classes (overrides order).
 
     spins0: int8[R, nspins] copied to every slice (tile=True, the reference's
             np.tile(spinVector, (P,1)).T start), or int8[R, slices, nspins] (tile=False), or None
@@ -117,8 +127,10 @@ def QuantumAnnealReplicas(sched, mcsteps, slices, temp, nspins, spins0, nbs, see
     if not 2 <= slices <= 64:
         raise ValueError("the packed colour path supports 2 <= slices <= 64 (got %d)" % slices)
     d = device or _dev.default_device()
+    orders = None
     if color is None:
-        color = _tools.ColourGraph(nbs)
+        color, orders = _resolve_order(order, nbs, sched.size * int(mcsteps), int(nspins),
+                                       int(seed) & 0xFFFFFFFF)
     d.set_graph(nbs, color)
     if int(nspins) != d.nspins:
         raise ValueError("nspins=%d but nbs describes %d spins" % (nspins, d.nspins))
@@ -128,7 +140,8 @@ def QuantumAnnealReplicas(sched, mcsteps, slices, temp, nspins, spins0, nbs, see
         d.state_init_random(seed, replica0, tile=True)
     else:
         d.state_upload_spins(spins0, tile=tile)
-    d.qa_colour(sched, int(mcsteps), temp, seed, replica0=replica0, trotter=TROTTER[trotter])
+    d.qa_colour(sched, int(mcsteps), temp, seed, replica0=replica0, trotter=TROTTER[trotter],
+                orders=orders)
     out = {"energies": None, "words": None}
     if energies:
         out["energies"] = d.energy(download=download)

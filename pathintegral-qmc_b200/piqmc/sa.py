@@ -114,8 +114,8 @@ def Anneal_parallel(sched, mcsteps, svec, nbs, nthreads=1, device=None):
     svec = _f64(svec, 1, "svec")
     libc = ctypes.CDLL(None)
     seed = (libc.rand() << 31) | libc.rand()
-    out = AnnealReplicas(sched, mcsteps, _spins_i8(svec, "svec")[None], nbs, seed, device=device,
-                         energies=False)
+    out = AnnealReplicas(sched, mcsteps, _spins_i8(svec, "svec")[None], nbs, seed, order="natural",
+                         device=device, energies=False)
     svec[:] = out["spins"][0]
     return None
 
@@ -166,18 +166,43 @@ def Anneal_multispin(sched, mcsteps, svec_mat, nbs, rng, device=None):
     return None
 
 
-def AnnealReplicas(sched, mcsteps, spins0, nbs, seed, color=None, row0=0, device=None,
-                   energies=True, nreplicas=None):
-    """Production SA: R independent replicas, 64 per uint64 word, colour-parallel Metropolis with
+def _resolve_order(order, nbs, nsweeps, nspins, order_seed):
+    """-> (color or None, orders or None) for the `order` option of the production paths."""
+    if isinstance(order, str):
+        if order == "permutation":
+            prng = np.random.RandomState(order_seed)
+            return None, np.stack([prng.permutation(nspins) for _ in range(nsweeps)]).astype(np.int32)
+        if order in ("natural", "checkerboard"):
+            return _tools.ColourGraph(nbs, order), None
+        raise ValueError("order must be 'natural', 'checkerboard', 'permutation' or an int array")
+    o = np.asarray(order)
+    if o.ndim == 1:
+        return _tools.ColourGraph(nbs, o), None
+    return None, np.ascontiguousarray(o, dtype=np.int32)
+
+
+def AnnealReplicas(sched, mcsteps, spins0, nbs, seed, order="permutation", color=None, row0=0,
+                   device=None, energies=True, nreplicas=None):
+    """Production SA: R independent replicas, 64 per uint64 word, colour-class Metropolis with
     Philox4x32-10 uniforms keyed by (seed; spin, replica, sweep).  sa.Anneal rules (float32 local
     field in table order, `>= 0` shortcut, temperature schedule).
 
+    order: the sequential sweep each colour-class sweep is equivalent to --
+        "permutation"  a fresh random permutation per sweep, as sa.Anneal (sa.pyx:100,120); the
+                       permutations come from RandomState(seed) and are shared by all replicas;
+        "natural"      0..N-1, as sa.Anneal_parallel with one thread (sa.pyx:248);
+        "checkerboard" fewest classes (fastest; not equivalent to a reference order);
+        int32[N] / int32[nsweeps,N]  explicit visiting order(s).
+    color: explicit colour classes (overrides order).
     spins0: int8[R,N] (+-1) or None for a Philox-generated random start (then give nreplicas).
     Returns dict(spins=int8[R,N], energies=float64[R] or None, words=uint64[G,N])."""
     sched = np.ascontiguousarray(sched, dtype=np.float64)
     d = device or _dev.default_device()
+    nsweeps = sched.size * int(mcsteps)
+    nspins = np.asarray(nbs).shape[0]
+    orders = None
     if color is None:
-        color = _tools.ColourGraph(nbs)
+        color, orders = _resolve_order(order, nbs, nsweeps, nspins, int(seed) & 0xFFFFFFFF)
     d.set_graph(nbs, color)
     n = d.nspins
     R = int(nreplicas) if spins0 is None else int(np.asarray(spins0).shape[0])
@@ -189,7 +214,7 @@ def AnnealReplicas(sched, mcsteps, spins0, nbs, seed, color=None, row0=0, device
         s = np.ones((G * 64, n), dtype=np.int8)
         s[:R] = _spins_i8(np.asarray(spins0), "spins0")
         d.state_upload_spins(s.reshape(G, 64, n), tile=False)
-    d.sa_colour(sched, int(mcsteps), seed, row0=row0)
+    d.sa_colour(sched, int(mcsteps), seed, row0=row0, orders=orders)
     en = d.energy().reshape(-1)[:R] if energies else None
     words = d.state_download_words()
     spins = _tools.UnpackWords(words, 64).reshape(G * 64, n)[:R]

@@ -8,7 +8,7 @@ import numpy as np
 import scipy.sparse as sps
 
 __all__ = ["bits2spins", "spins2bits", "GenerateNeighbors", "Generate2DIsingInstance",
-           "ColourGraph", "LoadIsingInstance", "IsingFromTriples", "GaussianTorusNeighbors",
+           "ColourGraph", "OrderLevels", "LoadIsingInstance", "IsingFromTriples", "GaussianTorusNeighbors", "TorusNaturalLevels",
            "PackWords", "UnpackWords"]
 
 
@@ -98,17 +98,47 @@ def Generate2DIsingInstance(nRows, rng):
 # ---------------------------------------------------------------------------------------------
 # Additions for the B200 kernels (no counterpart in the reference)
 # ---------------------------------------------------------------------------------------------
-def ColourGraph(nbs):
-    """Proper colouring of the graph described by a neighbour table: int32[N] with colours
-    0..C-1 such that no two spins joined by a non-zero coupling share a colour.  Self entries
-    (local fields) and zero couplings (pad rows) are ignored.  Bipartite graphs (the even-L
-    tori, bipartite8, boixo) get 2 colours by breadth-first search; anything else falls back to
-    greedy colouring in largest-degree-first order (K_n -> n colours)."""
+def _adjacency(nbs):
     nbs = np.asarray(nbs)
-    n, maxnb = nbs.shape[0], nbs.shape[1]
+    n = nbs.shape[0]
     idx = nbs[:, :, 0].astype(np.int64)
     live = (nbs[:, :, 1] != 0.0) & (idx != np.arange(n)[:, None])
-    adj = [idx[i][live[i]].tolist() for i in range(n)]
+    return [idx[i][live[i]].tolist() for i in range(n)]
+
+
+def OrderLevels(nbs, order=None):
+    """Level colouring of a sequential visiting order: level[i] = 1 + max(level[j]) over coupled
+    neighbours j visited before i (0 if there is none).  Updating level 0, then level 1, ... with
+    all spins of a level at once is EXACTLY the sequential sweep in that order: every spin sees
+    the new value of the neighbours visited before it and the old value of the others.  This is
+    how the colour-class kernels reproduce the reference's natural-order sweep
+    (piqmc/qmc.pyx:320, QuantumAnneal_parallel) and permutation-order sweeps (piqmc/sa.pyx:100).
+    order: None = natural order 0..N-1, or an int array (order[t] = spin visited at step t)."""
+    adj = _adjacency(nbs)
+    n = len(adj)
+    level = -np.ones(n, dtype=np.int32)
+    for i in (range(n) if order is None else np.asarray(order).tolist()):
+        m = -1
+        for j in adj[i]:
+            if level[j] > m:
+                m = level[j]
+        level[i] = m + 1
+    return level
+
+
+def ColourGraph(nbs, order=None):
+    """Colour classes for the colour-parallel kernels: int32[N], classes are swept in ascending
+    colour index and no two spins joined by a non-zero coupling share a class.  Self entries
+    (local fields) and zero couplings (pad rows) are ignored.
+
+    order=None or "checkerboard": fewest classes -- 2 by breadth-first search when the graph is
+        bipartite (the even-L tori, bipartite8, boixo), else greedy largest-degree-first (K_n -> n).
+    order="natural" or an int array: the dependency levels of that sequential visiting order
+        (OrderLevels): the sweep then equals the sequential sweep in that order."""
+    if order is not None and not (isinstance(order, str) and order == "checkerboard"):
+        return OrderLevels(nbs, None if isinstance(order, str) and order == "natural" else order)
+    adj = _adjacency(nbs)
+    n = len(adj)
     color = -np.ones(n, dtype=np.int32)
     bipartite = True
     for s in range(n):
@@ -135,8 +165,7 @@ def ColourGraph(nbs):
     if bipartite:
         return color
     color[:] = -1
-    order = sorted(range(n), key=lambda i: -len(adj[i]))
-    for i in order:
+    for i in sorted(range(n), key=lambda i: -len(adj[i])):
         used = {color[j] for j in adj[i] if color[j] >= 0}
         c = 0
         while c in used:
@@ -189,6 +218,13 @@ def GaussianTorusNeighbors(L, seed=2024, dtype=np.float32):
     else:
         color = ColourGraph(nbs)
     return nbs, color
+
+
+def TorusNaturalLevels(L):
+    """OrderLevels(nbs, None) of an L x L torus numbered row-major, in closed form: the
+    anti-diagonals level(y, x) = x + y (2L-1 classes)."""
+    i = np.arange(L * L)
+    return ((i // L) + (i % L)).astype(np.int32)
 
 
 def PackWords(spins):
