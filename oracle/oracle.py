@@ -286,3 +286,12 @@ def ref():
     if d not in sys.path:
         sys.path.insert(0, d)
     return importlib.import_module("piqmc_ref")
+
+
+def colour_counters(reset=False):
+    """(attempts, attempts that needed a uniform) of the colour-semantics functions so far."""
+    arr = (ctypes.c_uint64 * 2).in_dll(lib(), "oracle_colour_counters")
+    out = (int(arr[0]), int(arr[1]))
+    if reset:
+        arr[0] = arr[1] = 0
+    return out
