@@ -45,16 +45,19 @@ void free_graph(piqmc_ctx *c)
     free_dev(c->d_idx_t);
     free_dev(c->d_J32_t);
     free_dev(c->d_members);
-    free_dev(c->d_lut);
+    free_dev(c->d_level);
+    free_dev(c->d_done);
+    c->flow_nchunks = 0;
     c->color_off.clear();
     c->nspins = c->maxnb = c->ncolors = 0;
-    c->lut_ok = false;
 }
 
 void free_state(piqmc_ctx *c)
 {
     free_dev(c->d_words);
     free_dev(c->d_energy);
+    free_dev(c->d_done);            // completion flags belong to a state
+    c->flow_nchunks = 0;
     c->nrows = c->lanes = 0;
 }
 
@@ -127,6 +130,7 @@ static int apply_colouring(piqmc_ctx *h, int ncolors, const int32_t *color, bool
     PIQMC_CUDA(cudaStreamSynchronize(h->stream));     // the old lists may still be in use
     PIQMC_CUDA(cudaMemcpy(h->d_members, members.data(), (size_t)h->nspins * sizeof(int32_t),
                           cudaMemcpyHostToDevice));
+    PIQMC_CUDA(cudaMemcpy(h->d_level, color, (size_t)h->nspins * sizeof(int32_t), cudaMemcpyHostToDevice));
     h->ncolors = ncolors;
     return PIQMC_OK;
 }
@@ -174,9 +178,36 @@ static int run_colour_sweeps(piqmc_ctx *h, int qa, int trotter, int nsched, int 
                              uint32_t row0, uint32_t sweep0, const int32_t *orders)
 {
     const int N = h->nspins;
-    uint32_t sweep = sweep0;
+    const size_t nsweeps = (size_t)nsched * mcsteps;
+    if (nsweeps == 0) return PIQMC_OK;
+    const bool fast = piqmc_fast_ok(h, qa, trotter);
+    if (!orders) PIQMC_REQUIRE(h->ncolors > 0, PIQMC_ENOGRAPH, "graph has no colouring");
+    else TRY(check_orders(N, nsweeps, orders));
+
+    // per-sweep parameters (fast path)
+    DevBuf<float> d_jp2, d_invT;
+    if (fast) {
+        std::vector<float> a(nsweeps), b(nsweeps);
+        for (size_t s = 0; s < nsweeps; s++) {
+            a[s] = jp2[s / mcsteps];
+            b[s] = invT[s / mcsteps];
+        }
+        PIQMC_CUDA(d_jp2.alloc(nsweeps));
+        PIQMC_CUDA(d_invT.alloc(nsweeps));
+        PIQMC_CUDA(cudaMemcpyAsync(d_jp2.p, a.data(), nsweeps * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        PIQMC_CUDA(cudaMemcpyAsync(d_invT.p, b.data(), nsweeps * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        PIQMC_CUDA(cudaStreamSynchronize(h->stream));     // a, b are about to go out of scope
+    }
+
     if (!orders) {
-        PIQMC_REQUIRE(h->ncolors > 0, PIQMC_ENOGRAPH, "graph has no colouring");
+        if (fast) {
+            TRY(launch_fast_sweeps(h, qa, (int)nsweeps, h->d_members, h->d_level, 0, d_jp2.p, d_invT.p, seed,
+                                   row0, sweep0));
+            // the per-sweep parameter arrays must outlive the launch
+            PIQMC_CUDA(cudaStreamSynchronize(h->stream));
+            return PIQMC_OK;
+        }
+        uint32_t sweep = sweep0;
         for (int f = 0; f < nsched; f++)
             for (int s = 0; s < mcsteps; s++, sweep++)
                 for (int c = 0; c < h->ncolors; c++)
@@ -185,33 +216,41 @@ static int run_colour_sweeps(piqmc_ctx *h, int qa, int trotter, int nsched, int 
                                             sweep));
         return PIQMC_OK;
     }
-    // per-sweep visiting orders: level-colour each sweep on the host, ship the member lists in
-    // chunks (bounded device memory), launch level by level
-    const size_t nsweeps = (size_t)nsched * mcsteps;
-    TRY(check_orders(N, nsweeps, orders));
+
+    // per-sweep visiting orders: level-colour each sweep on the host, ship member lists (and
+    // levels) in chunks of sweeps (bounded device memory)
     const size_t chunk = std::max<size_t>(1, std::min<size_t>(nsweeps, (size_t)(64u << 20) / ((size_t)N * 4)));
-    DevBuf<int32_t> d_mem;
+    DevBuf<int32_t> d_mem, d_lev;
     PIQMC_CUDA(d_mem.alloc(chunk * N));
-    std::vector<int32_t> members(chunk * N), level(N);
+    if (fast) PIQMC_CUDA(d_lev.alloc(chunk * N));
+    std::vector<int32_t> members(chunk * N), levels(chunk * N);
     std::vector<std::vector<int>> offs(chunk);
     for (size_t base = 0; base < nsweeps; base += chunk) {
         const size_t m = std::min(chunk, nsweeps - base);
         for (size_t s = 0; s < m; s++) {
+            int32_t *lev = levels.data() + s * N;
             const int nlev = order_levels(N, h->maxnb, h->h_idx.data(), h->h_live.data(),
-                                          orders + (base + s) * N, level.data());
-            bucket_members(N, nlev, level.data(), offs[s], members.data() + s * N);
+                                          orders + (base + s) * N, lev);
+            bucket_members(N, nlev, lev, offs[s], members.data() + s * N);
         }
         PIQMC_CUDA(cudaStreamSynchronize(h->stream));     // previous chunk's lists no longer in use
         PIQMC_CUDA(cudaMemcpyAsync(d_mem.p, members.data(), m * N * sizeof(int32_t), cudaMemcpyHostToDevice,
                                    h->stream));
-        for (size_t s = 0; s < m; s++, sweep++) {
-            const int f = (int)((base + s) / mcsteps);
-            const std::vector<int> &off = offs[s];
-            for (size_t c = 0; c + 1 < off.size(); c++)
-                TRY(launch_colour_sweep(h, qa, trotter, d_mem.p + s * N + off[c], off[c + 1] - off[c], jp2[f],
-                                        invT[f], seed, row0, sweep));
+        if (fast) {
+            PIQMC_CUDA(cudaMemcpyAsync(d_lev.p, levels.data(), m * N * sizeof(int32_t), cudaMemcpyHostToDevice,
+                                       h->stream));
+            TRY(launch_fast_sweeps(h, qa, (int)m, d_mem.p, d_lev.p, 1, d_jp2.p + base, d_invT.p + base, seed, row0,
+                                   sweep0 + (uint32_t)base));
+        } else {
+            for (size_t s = 0; s < m; s++) {
+                const int f = (int)((base + s) / mcsteps);
+                const std::vector<int> &off = offs[s];
+                for (size_t c = 0; c + 1 < off.size(); c++)
+                    TRY(launch_colour_sweep(h, qa, trotter, d_mem.p + s * N + off[c], off[c + 1] - off[c], jp2[f],
+                                            invT[f], seed, row0, sweep0 + (uint32_t)(base + s)));
+            }
         }
-        PIQMC_CUDA(cudaStreamSynchronize(h->stream));     // d_mem / members are reused or freed next
+        PIQMC_CUDA(cudaStreamSynchronize(h->stream));     // lists are reused or freed next
     }
     return PIQMC_OK;
 }
@@ -262,6 +301,7 @@ int piqmc_destroy(piqmc_handle h)
     free_graph(h);
     free_state(h);
     free_dev(h->d_epart);
+    free_dev(h->d_ticket);
     cudaStreamDestroy(h->stream);
     delete h;
     return PIQMC_OK;
@@ -393,8 +433,8 @@ int piqmc_set_graph(piqmc_handle h, int nspins, int maxnb, const int32_t *idx, c
             h->h_live[e] = (idx[e] != i && J[e] != 0.0) ? 1 : 0;
         }
     PIQMC_CUDA(cudaMalloc(&h->d_members, (size_t)nspins * sizeof(int32_t)));
+    PIQMC_CUDA(cudaMalloc(&h->d_level, (size_t)nspins * sizeof(int32_t)));
     if (color) TRY(apply_colouring(h, ncolors, color, false));
-    TRY(build_lut(h));
     // a new graph invalidates any resident state
     free_state(h);
     return PIQMC_OK;

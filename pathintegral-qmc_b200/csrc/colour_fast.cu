@@ -1,0 +1,442 @@
+// colour_fast.cu -- the production Metropolis sweep kernel (maxnb <= 4; QA with the reference's
+// Trotter neighbours, or SA), one launch for a whole run of sweeps.
+//
+// Work unit = block = (sweep s, spin i, chunk of rows).  Within a sweep the spins are ordered by
+// colour class ("level"); a unit may run as soon as, for the same chunk of rows,
+//     every coupled neighbour of a LOWER level has finished sweep s       (it reads their new value)
+//     every coupled neighbour of a HIGHER level has finished sweep s-1    (it reads their old value
+//                                                                          and they have read ours)
+//     the spin itself has finished sweep s-1.
+// Completion is published in done[spin][chunk] = tag(s) with release/acquire ordering, so the
+// sweeps need no kernel boundary and no grid barrier: colour classes, and successive sweeps,
+// overlap like a wavefront.  Units are handed out by an atomic ticket in (sweep, level) order,
+// so a unit only ever waits for units with smaller tickets, which are already resident or done:
+// the scheme cannot deadlock whatever the hardware's block dispatch order.
+//
+// Per unit: (1) the per-spin decision tables are built in shared memory while the unit waits;
+// (2) each thread owns one 64-lane word per pass: the 2*NC boolean functions "accept by sign" /
+// "needs a uniform" of the 4 neighbour-disagreement masks are evaluated for all 64 lanes at once
+// in algebraic normal form; (3) the few words with lanes that need a uniform are resolved
+// cooperatively by the warp (one Philox block per thread).  Semantics: oracle_qa_colour /
+// oracle_sa_colour (oracle/piqmc_oracle.c part 3), bit for bit.
+#include "common.cuh"
+
+namespace {
+
+constexpr int FAST_THREADS = 128;
+constexpr int FAST_WARPS = FAST_THREADS / 32;
+constexpr int QCAP = 64;            // pooled draw requests per warp and pass
+constexpr int COOP_MIN = 4;         // words with at least this many needy lanes are drawn by the whole warp
+
+__device__ __forceinline__ float flip_sign(float negJ2, uint32_t bit)
+{
+    return __int_as_float(__float_as_int(negJ2) ^ (int)(bit << 31));
+}
+
+__device__ __forceinline__ uint32_t pick(const u32x4 &r, int q)
+{
+    return q == 0 ? r.x : (q == 1 ? r.y : (q == 2 ? r.z : r.w));
+}
+
+// the uniform of (row, lane, spin, sweep): Philox block (spin, lane>>2, sweep, row), word lane&3
+__device__ __forceinline__ uint32_t lane_uniform(int lane, uint32_t spin, uint32_t sweep, uint32_t prow,
+                                                 uint32_t k0, uint32_t k1)
+{
+    return pick(philox4x32_10(spin, (uint32_t)(lane >> 2) | (PIQMC_STREAM_SWEEP << 16), sweep, prow, k0, k1),
+                lane & 3);
+}
+
+struct SpinTable {
+    uint32_t cacc[3][16];    // ANF coefficient masks (0 / ~0) of "accept by sign", per Trotter class
+    uint32_t cneed[3][16];   // ... of "needs a uniform"
+    uint32_t thr[3][16];     // acceptance threshold of pattern p in class c
+    uint32_t hacc[3], hneed[3];   // truth tables (bit p)
+};
+
+// Per-spin decision tables.  Trotter class of a lane = number of Trotter neighbours it disagrees
+// with (0,1,2): tsum = -2*jp2, +0, +2*jp2.  Ends with a __syncthreads().
+template <bool QA>
+__device__ __forceinline__ void build_table(SpinTable &tab, int i, int nspins, int maxnb,
+                                            const float *__restrict__ J_t, float jp2, float invT)
+{
+    constexpr int NC = QA ? 3 : 1;
+    if (threadIdx.x < NC * 16) {
+        const int c = threadIdx.x / 16, p = threadIdx.x % 16;
+        float e = 0.0f;
+        for (int n = 0; n < maxnb; n++)
+            e = __fadd_rn(e, flip_sign(-2.0f * J_t[(size_t)n * nspins + i], (uint32_t)(p >> n) & 1u));
+        if (QA) {
+            const float tsum = (c == 0) ? -2.0f * jp2 : (c == 1 ? 0.0f : 2.0f * jp2);   // exact
+            e = __fadd_rn(e, tsum);
+        }
+        e = __fadd_rn(e, 0.0f);
+        const bool acc = QA ? (e > 0.0f) : (e >= 0.0f);
+        const float x = __fmul_rn(e, invT);
+        const bool need = !acc && (x >= PIQMC_XCUT);
+        tab.thr[c][p] = need ? colour_thresh(x) : 0u;
+        // truth tables by ballot: 16 consecutive lanes of a warp hold one class
+        const uint32_t ba = __ballot_sync(__activemask(), acc), bn = __ballot_sync(__activemask(), need);
+        if (p == 0) {
+            const int sh = (threadIdx.x & 16);
+            tab.hacc[c] = (ba >> sh) & 0xFFFFu;
+            tab.hneed[c] = (bn >> sh) & 0xFFFFu;
+        }
+    }
+    __syncthreads();
+    // Moebius transform: ANF coefficient of monomial S = parity of the truth table over subsets of S
+    if (threadIdx.x < NC * 32) {
+        const int c = threadIdx.x / 32, f = (threadIdx.x / 16) & 1, S = threadIdx.x % 16;
+        uint32_t sub = 1u;                       // bit T set <=> T is a subset of S
+        if (S & 1) sub |= sub << 1;
+        if (S & 2) sub |= sub << 2;
+        if (S & 4) sub |= sub << 4;
+        if (S & 8) sub |= sub << 8;
+        const uint32_t h = f ? tab.hneed[c] : tab.hacc[c];
+        const uint32_t coef = (__popc(h & sub) & 1) ? 0xFFFFFFFFu : 0u;
+        if (f) tab.cneed[c][S] = coef;
+        else   tab.cacc[c][S] = coef;
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ uint32_t pattern_at(const uint64_t (&x)[4], int k)
+{
+    return (uint32_t)((x[0] >> k) & 1) | (uint32_t)((x[1] >> k) & 1) << 1 |
+           (uint32_t)((x[2] >> k) & 1) << 2 | (uint32_t)((x[3] >> k) & 1) << 3;
+}
+
+__device__ __forceinline__ uint64_t shfl64(uint64_t v, int src)
+{
+    const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src);
+    const uint32_t hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+// Resolve the lanes in NEED (those whose Metropolis test needs a uniform); returns the accepted
+// ones.  Must be called by all 32 threads of a warp.  Needy lanes cluster: the slices of one
+// replica are strongly correlated, so a word has either none or most of its 64 lanes needy.
+//   (a) a word with >= COOP_MIN needy lanes is broadcast to the warp; thread l draws slices
+//       2l and 2l+1 (one Philox block), results come back by warp OR-reduction;
+//   (b) the remaining scattered lanes are pooled in a per-warp queue and drawn 32 at a time.
+// All loops have warp-uniform trip counts (a per-thread `while (mask)` would make the hardware
+// run the threads' iterations one after another).
+template <bool QA>
+__device__ __forceinline__ uint64_t resolve_draws(uint64_t NEED, const uint64_t (&x)[4], uint64_t XL, uint64_t XR,
+                                                  const SpinTable &tab, uint2 *queue, uint32_t spin,
+                                                  uint32_t sweep, uint32_t prow_warp, uint32_t k0, uint32_t k1)
+{
+    const int lane = threadIdx.x & 31;
+    uint64_t ACC = 0;
+    uint32_t big = __ballot_sync(0xffffffffu, __popcll(NEED) >= COOP_MIN);
+    while (big) {                                                   // warp-uniform
+        const int src = __ffs(big) - 1;
+        big &= big - 1;
+        const uint64_t needs = shfl64(NEED, src);
+        uint64_t xs[4];
+#pragma unroll
+        for (int n = 0; n < 4; n++) xs[n] = shfl64(x[n], src);
+        const uint64_t xls = QA ? shfl64(XL, src) : 0ull, xrs = QA ? shfl64(XR, src) : 0ull;
+        const int ka = 2 * lane;
+        const uint32_t need2 = (uint32_t)(needs >> ka) & 3u;
+        uint32_t acc2 = 0;
+        if (need2) {
+            const u32x4 r = philox4x32_10(spin, (uint32_t)(ka >> 2) | (PIQMC_STREAM_SWEEP << 16), sweep,
+                                          prow_warp + (uint32_t)src, k0, k1);
+#pragma unroll
+            for (int b = 0; b < 2; b++) {
+                const int k = ka + b;
+                const uint32_t c = QA ? (uint32_t)((xls >> k) & 1) + (uint32_t)((xrs >> k) & 1) : 0u;
+                const uint32_t u = (ka & 2) ? (b ? r.w : r.z) : (b ? r.y : r.x);
+                if (((need2 >> b) & 1u) && u < tab.thr[c][pattern_at(xs, k)]) acc2 |= 1u << b;
+            }
+        }
+        const uint32_t lo = __reduce_or_sync(0xffffffffu, lane < 16 ? acc2 << (2 * lane) : 0u);
+        const uint32_t hi = __reduce_or_sync(0xffffffffu, lane >= 16 ? acc2 << (2 * lane - 32) : 0u);
+        if (lane == src) {
+            ACC |= ((uint64_t)hi << 32) | lo;
+            NEED = 0;
+        }
+    }
+    while (true) {
+        const int n = __popcll(NEED);
+        int incl = n;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total == 0) break;
+        const int excl = incl - n;
+        uint64_t mask = NEED;
+        int pos = excl;
+#pragma unroll
+        for (int j = 0; j < COOP_MIN - 1; j++) {                    // n < COOP_MIN here
+            if (mask && pos < QCAP) {
+                const int k = __ffsll((long long)mask) - 1;
+                mask &= mask - 1;
+                const uint32_t c = QA ? (uint32_t)((XL >> k) & 1) + (uint32_t)((XR >> k) & 1) : 0u;
+                queue[pos++] = make_uint2(tab.thr[c][pattern_at(x, k)], (uint32_t)lane | ((uint32_t)k << 5));
+            }
+        }
+        const uint64_t taken = NEED ^ mask;
+        __syncwarp();
+        const int T = total < QCAP ? total : QCAP;
+        uint32_t res[QCAP / 32];
+#pragma unroll
+        for (int r = 0; r < QCAP / 32; r++) {
+            res[r] = 0u;
+            if (r * 32 < T) {                                       // warp-uniform
+                bool a = false;
+                const int it = r * 32 + lane;
+                if (it < T) {
+                    const uint2 q = queue[it];
+                    a = lane_uniform((int)(q.y >> 5), spin, sweep, prow_warp + (q.y & 31u), k0, k1) < q.x;
+                }
+                res[r] = __ballot_sync(0xffffffffu, a);
+            }
+        }
+        uint64_t tk = taken;
+        pos = excl;
+#pragma unroll
+        for (int j = 0; j < COOP_MIN - 1; j++) {
+            if (tk) {
+                const int k = __ffsll((long long)tk) - 1;
+                tk &= tk - 1;
+                const uint32_t word = (pos < 32) ? res[0] : res[QCAP / 32 - 1];
+                if ((word >> (pos & 31)) & 1u) ACC |= 1ull << k;
+                pos++;
+            }
+        }
+        NEED = mask;
+        __syncwarp();
+    }
+    return ACC;
+}
+
+__device__ __forceinline__ uint32_t ld_acquire(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void st_release(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+struct FastArgs {
+    uint64_t *words;            // [N][nrows]
+    const int32_t *idx_t;       // [maxnb][N]
+    const float *J_t;           // [maxnb][N]
+    const int32_t *members;     // per sweep (or shared): spins in level-major order
+    const int32_t *level;       // per sweep (or shared): level of every spin
+    const float *jp2, *invT;    // per sweep
+    uint32_t *done;             // [N][nchunks] tag of the last finished sweep
+    unsigned int *ticket;
+    int nspins, nrows, maxnb, lanes, nchunks, rows_per_block;
+    int per_sweep_lists;        // members/level advance by N per sweep
+    uint32_t k0, k1, row0, sweep0, tag0;
+    unsigned int ticket_base;   // units handed out by earlier launches of the same run
+};
+
+template <bool QA>
+__global__ void __launch_bounds__(FAST_THREADS, 5) colour_sweep_fast(const FastArgs a)
+{
+    __shared__ SpinTable tab;
+    __shared__ uint2 queues[FAST_WARPS][QCAP];
+    __shared__ unsigned int s_ticket;
+    constexpr int NC = QA ? 3 : 1;
+
+    if (threadIdx.x == 0) s_ticket = atomicAdd(a.ticket, 1u) - a.ticket_base;
+    __syncthreads();
+    const unsigned int t = s_ticket;
+    const unsigned int per_sweep = (unsigned int)a.nspins * (unsigned int)a.nchunks;
+    const int s = (int)(t / per_sweep);
+    const unsigned int rem = t - (unsigned int)s * per_sweep;
+    const int chunk = (int)(rem % (unsigned int)a.nchunks);
+    const size_t lbase = a.per_sweep_lists ? (size_t)s * a.nspins : 0;
+    const int i = a.members[lbase + rem / (unsigned int)a.nchunks];
+    const uint32_t tag = a.tag0 + (uint32_t)s + 1u;
+    const uint32_t sweep = a.sweep0 + (uint32_t)s;
+    const int nspins = a.nspins, nrows = a.nrows, maxnb = a.maxnb, lanes = a.lanes;
+
+    build_table<QA>(tab, i, nspins, maxnb, a.J_t, a.jp2[s], a.invT[s]);
+
+    int nb[4];
+#pragma unroll
+    for (int n = 0; n < 4; n++) nb[n] = (n < maxnb) ? a.idx_t[(size_t)n * nspins + i] : i;
+
+    // ---- wait until this unit's inputs are final (see the header comment)
+    if (threadIdx.x <= 4) {
+        int j = i;
+        uint32_t want = tag - 1u;
+        bool must = true;
+        if (threadIdx.x < 4) {
+            j = nb[threadIdx.x];
+            must = threadIdx.x < maxnb && j != i && a.J_t[(size_t)threadIdx.x * nspins + i] != 0.0f;
+            if (must && a.level[lbase + j] < a.level[lbase + i]) want = tag;
+        }
+        if (must) {
+            const uint32_t *flag = a.done + (size_t)j * a.nchunks + chunk;
+            while ((int32_t)(ld_acquire(flag) - want) < 0) __nanosleep(64);
+        }
+    }
+    __syncthreads();
+
+    const int rbeg = chunk * a.rows_per_block;
+    const int rend = min(nrows, rbeg + a.rows_per_block);
+    const uint64_t valid = (lanes >= 64) ? ~0ull : ((1ull << lanes) - 1ull);
+    uint2 *queue = queues[threadIdx.x >> 5];
+    uint64_t *words = a.words;
+
+    for (int base = rbeg; base < rend; base += FAST_THREADS) {     // block-uniform trip count
+        const int row = base + threadIdx.x;
+        const bool live = row < rend;
+        uint64_t *wrow = words + row;
+        // L2-only loads: another unit may have rewritten these words during this very launch
+        const uint64_t w = live ? __ldcg(wrow + (size_t)i * nrows) : 0ull;
+        const uint32_t prow_warp = a.row0 + (uint32_t)(base + (threadIdx.x & ~31));
+        uint64_t x[4];
+#pragma unroll
+        for (int n = 0; n < 4; n++)          // self entries (local fields) and unused columns: x = w / 0
+            x[n] = (live && n < maxnb) ? ((nb[n] == i) ? w : (w ^ __ldcg(wrow + (size_t)nb[n] * nrows))) : 0ull;
+
+        // ---- the 2*NC boolean functions of the neighbour pattern, all 64 lanes at once (ANF)
+        uint64_t Fa[NC], Fn[NC];
+        {
+            uint32_t mlo[16], mhi[16];
+            mlo[0] = mhi[0] = 0xFFFFFFFFu;
+#pragma unroll
+            for (int n = 0; n < 4; n++) {
+                const uint32_t lo = (uint32_t)x[n], hi = (uint32_t)(x[n] >> 32);
+#pragma unroll
+                for (int S = 0; S < (1 << n); S++) {
+                    mlo[(1 << n) + S] = S ? (mlo[S] & lo) : lo;
+                    mhi[(1 << n) + S] = S ? (mhi[S] & hi) : hi;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                uint32_t alo = tab.cacc[c][0], ahi = alo, nlo = tab.cneed[c][0], nhi = nlo;
+#pragma unroll
+                for (int S = 1; S < 16; S++) {
+                    const uint32_t ca = tab.cacc[c][S], cn = tab.cneed[c][S];
+                    alo ^= ca & mlo[S];
+                    ahi ^= ca & mhi[S];
+                    nlo ^= cn & mlo[S];
+                    nhi ^= cn & mhi[S];
+                }
+                Fa[c] = ((uint64_t)ahi << 32) | alo;
+                Fn[c] = ((uint64_t)nhi << 32) | nlo;
+            }
+        }
+
+        uint64_t ACC, NEED, XL = 0, XR = 0, flips = 0;
+        if (QA) {
+            // reference Trotter neighbours: slices P-1 (old value for everyone; itself for lane P-1)
+            // and 1 (old for lane 0, itself for lane 1, new for lanes >= 2): decide lane 1 first.
+            const uint64_t bl = ((w >> (lanes - 1)) & 1ull) ? ~0ull : 0ull;
+            const uint64_t br_old = ((w >> 1) & 1ull) ? ~0ull : 0ull;
+            XL = (w ^ bl) & ~(1ull << (lanes - 1));
+            {
+                const uint32_t c1 = (uint32_t)(XL >> 1) & 1u;           // lane 1: right neighbour is itself
+                const uint64_t one = live ? 2ull : 0ull;
+                flips = (c1 ? Fa[1] : Fa[0]) & one;
+                if ((c1 ? Fn[1] : Fn[0]) & one)                          // ~1% of the words
+                    if (lane_uniform(1, (uint32_t)i, sweep, a.row0 + (uint32_t)row, a.k0, a.k1) <
+                        tab.thr[c1][pattern_at(x, 1)])
+                        flips = 2ull;
+            }
+            const uint64_t br_new = br_old ^ ((flips & 2ull) ? ~0ull : 0ull);
+            XR = ((w ^ br_new) & ~1ull) | ((w ^ br_old) & 1ull);       // lane 0 sees the old bit 1
+            const uint64_t todo = live ? (valid & ~2ull) : 0ull;
+            const uint64_t C0 = ~(XL | XR), C1 = XL ^ XR, C2 = XL & XR;
+            ACC = ((C0 & Fa[0]) | (C1 & Fa[1]) | (C2 & Fa[NC - 1])) & todo;
+            NEED = ((C0 & Fn[0]) | (C1 & Fn[1]) | (C2 & Fn[NC - 1])) & todo;
+        } else {
+            const uint64_t todo = live ? valid : 0ull;
+            ACC = Fa[0] & todo;
+            NEED = Fn[0] & todo;
+        }
+        if (__any_sync(0xffffffffu, NEED != 0))
+            ACC |= resolve_draws<QA>(NEED, x, XL, XR, tab, queue, (uint32_t)i, sweep, prow_warp, a.k0, a.k1);
+        if (live) wrow[(size_t)i * nrows] = w ^ flips ^ ACC;
+    }
+
+    // ---- publish: all stores of the block happen-before the flag
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        st_release(a.done + (size_t)i * a.nchunks + chunk, tag);
+    }
+}
+
+}  // namespace
+
+// Runs `nsweeps` sweeps in as few launches as the grid-size limit allows (normally one).
+// members/level: device arrays, level-major spin order and level per spin; either one list for
+// all sweeps or one per sweep.  d_jp2/d_invT: per sweep.
+int launch_fast_sweeps(piqmc_ctx *c, int qa, int nsweeps, const int32_t *d_members, const int32_t *d_level,
+                       int per_sweep_lists, const float *d_jp2, const float *d_invT, uint64_t seed,
+                       uint32_t row0, uint32_t sweep0)
+{
+    if (nsweeps <= 0) return PIQMC_OK;
+    // rows per block: the per-spin table is built once per block, so more rows per block is less
+    // overhead, but fewer independent chunks; keep >= 8 chunks when the state allows
+    int rpb = 512;
+    while (rpb > FAST_THREADS && (c->nrows + rpb - 1) / rpb < 8) rpb >>= 1;
+    const int nchunks = (c->nrows + rpb - 1) / rpb;
+    const size_t nflags = (size_t)c->nspins * nchunks;
+    if (c->flow_nchunks != nchunks || c->d_done == nullptr) {
+        PIQMC_CUDA(cudaStreamSynchronize(c->stream));
+        if (c->d_done) PIQMC_CUDA(cudaFree(c->d_done));
+        c->d_done = nullptr;
+        PIQMC_CUDA(cudaMalloc(&c->d_done, nflags * sizeof(uint32_t)));
+        PIQMC_CUDA(cudaMemsetAsync(c->d_done, 0, nflags * sizeof(uint32_t), c->stream));
+        c->flow_nchunks = nchunks;
+        c->flow_tag = 0;
+    }
+    if (!c->d_ticket) {
+        PIQMC_CUDA(cudaMalloc(&c->d_ticket, sizeof(unsigned int)));
+    }
+    PIQMC_CUDA(cudaMemsetAsync(c->d_ticket, 0, sizeof(unsigned int), c->stream));
+
+    FastArgs a;
+    a.words = c->d_words;
+    a.idx_t = c->d_idx_t;
+    a.J_t = c->d_J32_t;
+    a.done = c->d_done;
+    a.ticket = c->d_ticket;
+    a.nspins = c->nspins;
+    a.nrows = c->nrows;
+    a.maxnb = c->maxnb;
+    a.lanes = c->lanes;
+    a.nchunks = nchunks;
+    a.rows_per_block = rpb;
+    a.per_sweep_lists = per_sweep_lists;
+    a.k0 = (uint32_t)seed;
+    a.k1 = (uint32_t)(seed >> 32);
+    a.row0 = row0;
+
+    const size_t per_sweep = nflags;
+    const int max_sweeps = (int)std::max<size_t>(1, ((size_t)1 << 30) / per_sweep);
+    for (int s0 = 0; s0 < nsweeps; s0 += max_sweeps) {
+        const int ns = std::min(max_sweeps, nsweeps - s0);
+        a.members = d_members + (per_sweep_lists ? (size_t)s0 * c->nspins : 0);
+        a.level = d_level + (per_sweep_lists ? (size_t)s0 * c->nspins : 0);
+        a.jp2 = d_jp2 + s0;
+        a.invT = d_invT + s0;
+        a.sweep0 = sweep0 + (uint32_t)s0;
+        a.tag0 = c->flow_tag + (uint32_t)s0;
+        a.ticket_base = (unsigned int)((size_t)s0 * per_sweep);
+        dim3 block(FAST_THREADS), grid((unsigned)((size_t)ns * per_sweep));
+        if (qa) colour_sweep_fast<true><<<grid, block, 0, c->stream>>>(a);
+        else    colour_sweep_fast<false><<<grid, block, 0, c->stream>>>(a);
+        c->launches++;
+        PIQMC_CUDA(cudaGetLastError());
+    }
+    c->flow_tag += (uint32_t)nsweeps;
+    return PIQMC_OK;
+}

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -50,8 +51,12 @@ struct piqmc_ctx {
     std::vector<int> color_off;     // ncolors+1 offsets into d_members
     std::vector<int32_t> h_idx;     // host copies for level colourings of per-sweep orders
     std::vector<uint8_t> h_live;    // J != 0 && idx != self
-    bool lut_ok = false;            // graph qualifies for the table-lookup fast path
-    float *d_lut = nullptr;         // [N][16] in-slice partial sums per neighbour pattern (maxnb<=4)
+    int32_t *d_level = nullptr;     // colour (level) of every spin (static colouring)
+    // dataflow sweep kernel (colour_fast.cu)
+    uint32_t *d_done = nullptr;     // [N][flow_nchunks] tag of the last finished sweep
+    unsigned int *d_ticket = nullptr;
+    int flow_nchunks = 0;
+    uint32_t flow_tag = 0;
 
     // packed state
     int nrows = 0, lanes = 0;
@@ -130,4 +135,12 @@ int launch_colour_sweep(piqmc_ctx *c, int qa, int trotter, const int32_t *member
 int launch_energy(piqmc_ctx *c);
 int launch_energy_coo(piqmc_ctx *c, int nspins, int nnz, const int32_t *d_row, const int32_t *d_col,
                       const double *d_val, int nconfs, const int8_t *d_spins, double *d_out);
-int build_lut(piqmc_ctx *c);
+// the production kernel: nsweeps sweeps in one dataflow launch (colour_fast.cu)
+int launch_fast_sweeps(piqmc_ctx *c, int qa, int nsweeps, const int32_t *d_members, const int32_t *d_level,
+                       int per_sweep_lists, const float *d_jp2, const float *d_invT, uint64_t seed,
+                       uint32_t row0, uint32_t sweep0);
+// variant: 0 auto (fast when graph and state qualify), 1 generic, 2 fast-if-possible
+static inline bool piqmc_fast_ok(const piqmc_ctx *c, int qa, int trotter)
+{
+    return c->variant != 1 && c->maxnb <= 4 && c->nrows >= 32 && (!qa || trotter == 0);
+}
