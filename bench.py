@@ -204,9 +204,8 @@ def run_ours(args):
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
-    assert R_TOTAL % world == 0
-    R = R_TOTAL // world
-    replica0 = rank * R
+    from piqmc.shard import gather_energies, shard_replicas
+    replica0, R = shard_replicas(R_TOTAL, world, rank)
     n = L * L
     K, W = args.steps, args.warmup
 
@@ -253,25 +252,21 @@ def run_ours(args):
 
     # ---- final energies on device + the single gather (outside the timed region, reported)
     tg0 = time.perf_counter()
-    dev.energy(download=False)
-    dev.synchronize()
-    en_local = torch.as_tensor(dev.energy_device_array(), device="cuda")
     if dist is not None:
-        en_all = torch.empty((world,) + tuple(en_local.shape), dtype=en_local.dtype, device="cuda")
-        dist.all_gather_into_tensor(en_all, en_local.contiguous())
-        en = en_all.reshape(-1, P).cpu().numpy()
+        en = gather_energies(dev, R_TOTAL).cpu().numpy()      # NCCL all-gather of float64[R, P]
     else:
-        en = en_local.cpu().numpy()
+        en = dev.energy()
     gather_ms = 1e3 * (time.perf_counter() - tg0)
 
-    # ---- end to end through the public API with HOST buffers (H2D of the initial spins and
-    #      D2H of packed configurations + energies inside the timed region)
-    rng = np.random.RandomState(SEED + rank)
-    spins0 = (2 * rng.randint(2, size=(R, n)) - 1).astype(np.int8)
+    # ---- end to end through the public API with HOST buffers: H2D of the initial spins (pinned),
+    #      the anneal, the device energy reduction, D2H of packed configurations + energies
+    spins0 = device.pinned_empty((R, n), np.int8)
+    spins0[:] = (2 * np.random.RandomState(SEED + rank).randint(2, size=(R, n)) - 1).astype(np.int8)
+    words_out = device.pinned_empty((n, R), np.uint64)
     barrier()
     t0 = time.perf_counter()
     out = qmc.QuantumAnnealReplicas(sched, 1, P, TEMP, n, spins0, nbs, SEED, color=color, replica0=replica0,
-                                    device=dev, energies=True, download=True)
+                                    device=dev, energies=True, download=True, words_out=words_out)
     dev.synchronize()
     e2e_s = time.perf_counter() - t0
     if dist is not None:

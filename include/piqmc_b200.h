@@ -61,6 +61,10 @@ void       *piqmc_stream(piqmc_handle h);
 /* number of kernel launches this handle has issued so far */
 uint64_t    piqmc_launch_count(piqmc_handle h);
 
+/* page-locked host buffers (full-speed PCIe transfers for the batched entry points) */
+int         piqmc_host_alloc(uint64_t bytes, void **out);
+int         piqmc_host_free(void *p);
+
 /* ---- glibc rand() restated on the host (seeding helper for the deterministic paths) ---- */
 void    piqmc_rand_seed(piqmc_rand_state *s, unsigned int seed);     /* == srand(seed)       */
 int32_t piqmc_rand_next(piqmc_rand_state *s);                        /* == rand()            */
@@ -148,7 +152,7 @@ void *piqmc_energy_devptr(piqmc_handle h);
  * orders: NULL -> every sweep uses the graph's colouring; else orders[s*nspins + t] is the spin
  * visited at step t of sweep s (s < nsched*mcsteps): each sweep is run through the level
  * colouring of its own order and so equals the sequential sweep in that order.
- * Asynchronous on the handle's stream when orders == NULL. */
+ * Returns when the sweeps have finished. */
 int piqmc_qa_colour(piqmc_handle h, const double *sched, int nsched, int mcsteps, float temp,
                     uint64_t seed, uint32_t replica0, uint32_t sweep0, int trotter,
                     const int32_t *orders);

@@ -317,6 +317,19 @@ int piqmc_synchronize(piqmc_handle h)
 void *piqmc_stream(piqmc_handle h) { return h ? (void *)h->stream : nullptr; }
 uint64_t piqmc_launch_count(piqmc_handle h) { return h ? h->launches : 0; }
 
+int piqmc_host_alloc(uint64_t bytes, void **out)
+{
+    PIQMC_REQUIRE(out != nullptr, PIQMC_EINVAL, "null out");
+    PIQMC_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+    return PIQMC_OK;
+}
+
+int piqmc_host_free(void *p)
+{
+    if (p) PIQMC_CUDA(cudaFreeHost(p));
+    return PIQMC_OK;
+}
+
 // ---- glibc rand() on the host ---------------------------------------------------------------
 void piqmc_rand_seed(piqmc_rand_state *s, unsigned int seed)
 {

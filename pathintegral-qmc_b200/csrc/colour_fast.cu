@@ -53,50 +53,43 @@ struct SpinTable {
     uint32_t hacc[3], hneed[3];   // truth tables (bit p)
 };
 
-// Per-spin decision tables.  Trotter class of a lane = number of Trotter neighbours it disagrees
-// with (0,1,2): tsum = -2*jp2, +0, +2*jp2.  Ends with a __syncthreads().
+// Per-spin decision tables, built by warp c for Trotter class c without any block barrier
+// (the caller synchronises once).  Trotter class of a lane = number of Trotter neighbours it
+// disagrees with (0,1,2): tsum = -2*jp2, +0, +2*jp2.
 template <bool QA>
-__device__ __forceinline__ void build_table(SpinTable &tab, int i, int nspins, int maxnb,
-                                            const float *__restrict__ J_t, float jp2, float invT)
+__device__ __forceinline__ void build_table_warp(SpinTable &tab, int c, int i, int nspins, int maxnb,
+                                                 const float *__restrict__ J_t, float jp2, float invT)
 {
-    constexpr int NC = QA ? 3 : 1;
-    if (threadIdx.x < NC * 16) {
-        const int c = threadIdx.x / 16, p = threadIdx.x % 16;
-        float e = 0.0f;
-        for (int n = 0; n < maxnb; n++)
-            e = __fadd_rn(e, flip_sign(-2.0f * J_t[(size_t)n * nspins + i], (uint32_t)(p >> n) & 1u));
-        if (QA) {
-            const float tsum = (c == 0) ? -2.0f * jp2 : (c == 1 ? 0.0f : 2.0f * jp2);   // exact
-            e = __fadd_rn(e, tsum);
-        }
-        e = __fadd_rn(e, 0.0f);
-        const bool acc = QA ? (e > 0.0f) : (e >= 0.0f);
-        const float x = __fmul_rn(e, invT);
-        const bool need = !acc && (x >= PIQMC_XCUT);
-        tab.thr[c][p] = need ? colour_thresh(x) : 0u;
-        // truth tables by ballot: 16 consecutive lanes of a warp hold one class
-        const uint32_t ba = __ballot_sync(__activemask(), acc), bn = __ballot_sync(__activemask(), need);
-        if (p == 0) {
-            const int sh = (threadIdx.x & 16);
-            tab.hacc[c] = (ba >> sh) & 0xFFFFu;
-            tab.hneed[c] = (bn >> sh) & 0xFFFFu;
-        }
+    const int lane = threadIdx.x & 31;
+    const int p = lane & 15;                     // lanes 16..31 mirror lanes 0..15
+    float e = 0.0f;
+    for (int n = 0; n < maxnb; n++)
+        e = __fadd_rn(e, flip_sign(-2.0f * J_t[(size_t)n * nspins + i], (uint32_t)(p >> n) & 1u));
+    if (QA) {
+        const float tsum = (c == 0) ? -2.0f * jp2 : (c == 1 ? 0.0f : 2.0f * jp2);   // exact
+        e = __fadd_rn(e, tsum);
     }
-    __syncthreads();
+    e = __fadd_rn(e, 0.0f);
+    const bool acc = QA ? (e > 0.0f) : (e >= 0.0f);
+    const float x = __fmul_rn(e, invT);
+    const bool need = !acc && (x >= PIQMC_XCUT);
+    if (lane < 16) tab.thr[c][p] = need ? colour_thresh(x) : 0u;
+    const uint32_t ha = __ballot_sync(0xffffffffu, acc) & 0xFFFFu;     // truth tables (bit p)
+    const uint32_t hn = __ballot_sync(0xffffffffu, need) & 0xFFFFu;
+    if (lane == 0) {
+        tab.hacc[c] = ha;
+        tab.hneed[c] = hn;
+    }
     // Moebius transform: ANF coefficient of monomial S = parity of the truth table over subsets of S
-    if (threadIdx.x < NC * 32) {
-        const int c = threadIdx.x / 32, f = (threadIdx.x / 16) & 1, S = threadIdx.x % 16;
-        uint32_t sub = 1u;                       // bit T set <=> T is a subset of S
-        if (S & 1) sub |= sub << 1;
-        if (S & 2) sub |= sub << 2;
-        if (S & 4) sub |= sub << 4;
-        if (S & 8) sub |= sub << 8;
-        const uint32_t h = f ? tab.hneed[c] : tab.hacc[c];
-        const uint32_t coef = (__popc(h & sub) & 1) ? 0xFFFFFFFFu : 0u;
-        if (f) tab.cneed[c][S] = coef;
-        else   tab.cacc[c][S] = coef;
-    }
-    __syncthreads();
+    const int S = p;
+    uint32_t sub = 1u;                           // bit T set <=> T is a subset of S
+    if (S & 1) sub |= sub << 1;
+    if (S & 2) sub |= sub << 2;
+    if (S & 4) sub |= sub << 4;
+    if (S & 8) sub |= sub << 8;
+    const uint32_t coef = (__popc((lane < 16 ? ha : hn) & sub) & 1) ? 0xFFFFFFFFu : 0u;
+    if (lane < 16) tab.cacc[c][S] = coef;
+    else           tab.cneed[c][S] = coef;
 }
 
 __device__ __forceinline__ uint32_t pattern_at(const uint64_t (&x)[4], int k)
@@ -262,25 +255,30 @@ __global__ void __launch_bounds__(FAST_THREADS, 5) colour_sweep_fast(const FastA
     const uint32_t sweep = a.sweep0 + (uint32_t)s;
     const int nspins = a.nspins, nrows = a.nrows, maxnb = a.maxnb, lanes = a.lanes;
 
-    build_table<QA>(tab, i, nspins, maxnb, a.J_t, a.jp2[s], a.invT[s]);
-
     int nb[4];
 #pragma unroll
     for (int n = 0; n < 4; n++) nb[n] = (n < maxnb) ? a.idx_t[(size_t)n * nspins + i] : i;
 
-    // ---- wait until this unit's inputs are final (see the header comment)
-    if (threadIdx.x <= 4) {
-        int j = i;
-        uint32_t want = tag - 1u;
-        bool must = true;
-        if (threadIdx.x < 4) {
-            j = nb[threadIdx.x];
-            must = threadIdx.x < maxnb && j != i && a.J_t[(size_t)threadIdx.x * nspins + i] != 0.0f;
-            if (must && a.level[lbase + j] < a.level[lbase + i]) want = tag;
-        }
-        if (must) {
-            const uint32_t *flag = a.done + (size_t)j * a.nchunks + chunk;
-            while ((int32_t)(ld_acquire(flag) - want) < 0) __nanosleep(64);
+    // ---- warps 0..NC-1 build the decision tables while warp 3 waits until this unit's inputs
+    //      are final (see the header comment); one barrier joins them
+    const int warp = threadIdx.x >> 5;
+    if (warp < NC) {
+        build_table_warp<QA>(tab, warp, i, nspins, maxnb, a.J_t, a.jp2[s], a.invT[s]);
+    } else if (warp == FAST_WARPS - 1) {
+        const int q = threadIdx.x & 31;
+        if (q <= 4) {
+            int j = i;
+            uint32_t want = tag - 1u;
+            bool must = true;
+            if (q < 4) {
+                j = nb[q];
+                must = q < maxnb && j != i && a.J_t[(size_t)q * nspins + i] != 0.0f;
+                if (must && a.level[lbase + j] < a.level[lbase + i]) want = tag;
+            }
+            if (must) {
+                const uint32_t *flag = a.done + (size_t)j * a.nchunks + chunk;
+                while ((int32_t)(ld_acquire(flag) - want) < 0) __nanosleep(32);
+            }
         }
     }
     __syncthreads();
@@ -291,17 +289,39 @@ __global__ void __launch_bounds__(FAST_THREADS, 5) colour_sweep_fast(const FastA
     uint2 *queue = queues[threadIdx.x >> 5];
     uint64_t *words = a.words;
 
+    // software pipeline: the 5 words of the next pass are requested before this pass computes.
+    // L2-only loads (ld.global.cg): another unit may have rewritten these words during this very
+    // launch and L1 is not coherent.
+    uint64_t w_nx = 0, wn_nx[4] = {0, 0, 0, 0};
+    {
+        const int row = rbeg + threadIdx.x;
+        if (row < rend) {
+            w_nx = __ldcg(words + (size_t)i * nrows + row);
+#pragma unroll
+            for (int n = 0; n < 4; n++)
+                if (n < maxnb && nb[n] != i) wn_nx[n] = __ldcg(words + (size_t)nb[n] * nrows + row);
+        }
+    }
     for (int base = rbeg; base < rend; base += FAST_THREADS) {     // block-uniform trip count
         const int row = base + threadIdx.x;
         const bool live = row < rend;
         uint64_t *wrow = words + row;
-        // L2-only loads: another unit may have rewritten these words during this very launch
-        const uint64_t w = live ? __ldcg(wrow + (size_t)i * nrows) : 0ull;
-        const uint32_t prow_warp = a.row0 + (uint32_t)(base + (threadIdx.x & ~31));
+        const uint64_t w = w_nx;
         uint64_t x[4];
 #pragma unroll
-        for (int n = 0; n < 4; n++)          // self entries (local fields) and unused columns: x = w / 0
-            x[n] = (live && n < maxnb) ? ((nb[n] == i) ? w : (w ^ __ldcg(wrow + (size_t)nb[n] * nrows))) : 0ull;
+        for (int n = 0; n < 4; n++)          // self entries (local fields): x = w; unused columns: 0
+            x[n] = (live && n < maxnb) ? ((nb[n] == i) ? w : (w ^ wn_nx[n])) : 0ull;
+        {
+            const int rown = row + FAST_THREADS;
+            w_nx = 0;
+            if (rown < rend) {
+                w_nx = __ldcg(words + (size_t)i * nrows + rown);
+#pragma unroll
+                for (int n = 0; n < 4; n++)
+                    if (n < maxnb && nb[n] != i) wn_nx[n] = __ldcg(words + (size_t)nb[n] * nrows + rown);
+            }
+        }
+        const uint32_t prow_warp = a.row0 + (uint32_t)(base + (threadIdx.x & ~31));
 
         // ---- the 2*NC boolean functions of the neighbour pattern, all 64 lanes at once (ANF)
         uint64_t Fa[NC], Fn[NC];

@@ -38,6 +38,8 @@ SIGNATURES = {
     "piqmc_synchronize": (c_int, [c_void]),
     "piqmc_stream": (c_void, [c_void]),
     "piqmc_launch_count": (c_u64, [c_void]),
+    "piqmc_host_alloc": (c_int, [c_u64, P(c_void)]),
+    "piqmc_host_free": (c_int, [c_void]),
     "piqmc_rand_seed": (None, [P(RandState), ctypes.c_uint]),
     "piqmc_rand_next": (ctypes.c_int32, [P(RandState)]),
     "piqmc_rand_capture_libc": (c_int, [P(RandState)]),

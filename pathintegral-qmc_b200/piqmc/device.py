@@ -183,7 +183,8 @@ class Device:
 
     def state_upload_spins(self, spins, tile=True):
         """tile: spins int8[nrows,N] copied to every lane; else int8[nrows,lanes,N]."""
-        spins = np.ascontiguousarray(spins, dtype=np.int8)
+        if not (isinstance(spins, np.ndarray) and spins.dtype == np.int8 and spins.flags.c_contiguous):
+            spins = np.ascontiguousarray(spins, dtype=np.int8)
         want = (self.nrows, self.nspins) if tile else (self.nrows, self.lanes, self.nspins)
         if spins.shape != want:
             raise ValueError("spins must have shape %s" % (want,))
@@ -286,6 +287,33 @@ def default_device(index=0):
     if d is None:
         d = _default[index] = Device(index)
     return d
+
+
+class _Pinned:
+    def __init__(self, nbytes):
+        self.ptr = ctypes.c_void_p()
+        check(lib.piqmc_host_alloc(int(nbytes), ctypes.byref(self.ptr)))
+
+    def __del__(self):
+        try:
+            lib.piqmc_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype):
+    """NumPy array in page-locked host memory (cudaHostAlloc): host<->device copies of such
+    arrays run at full PCIe speed.  The memory is released when the array is collected."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    owner = _Pinned(n)
+    buf = (ctypes.c_char * max(n, 1)).from_address(owner.ptr.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    _PINNED[arr.__array_interface__["data"][0]] = owner      # keep alive with the process
+    return arr
+
+
+_PINNED = {}
 
 
 def order_levels(nbs, order=None):

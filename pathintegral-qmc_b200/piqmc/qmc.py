@@ -102,7 +102,7 @@ def QuantumAnneal_parallel(sched, mcsteps, slices, temp, nspins, confs, nbs, nth
 
 def QuantumAnnealReplicas(sched, mcsteps, slices, temp, nspins, spins0, nbs, seed, order="natural",
                           color=None, replica0=0, trotter="reference", device=None, energies=True,
-                          tile=True, nreplicas=None, download=True):
+                          tile=True, nreplicas=None, download=True, words_out=None):
     """Production PIQMC: R replicas x `slices` Trotter slices x nspins, one uint64 word per
     (replica, spin) holding all slices, colour-class Metropolis sweeps with Philox4x32-10 keyed by
     (seed; spin, slice, sweep, replica0 + r), J_perp recomputed per schedule step.
@@ -120,8 +120,10 @@ def QuantumAnnealReplicas(sched, mcsteps, slices, temp, nspins, spins0, nbs, see
     spins0: int8[R, nspins] copied to every slice (tile=True, the reference's
             np.tile(spinVector, (P,1)).T start), or int8[R, slices, nspins] (tile=False), or None
             for a Philox-generated random start (give nreplicas).
-    Returns dict(words=uint64[R,nspins] (bit k <-> slice k, set <-> spin -1),
-                 energies=float64[R,slices] ClassicalIsingEnergy of every slice)."""
+    words_out: optional C-contiguous uint64[nspins, R] host buffer (e.g. device.pinned_empty) that
+            receives the packed state in device layout.
+    Returns dict(words=uint64[R,nspins] (bit k <-> slice k, set <-> spin -1; a transposed view of
+                 the spin-major buffer), energies=float64[R,slices] ClassicalIsingEnergy per slice)."""
     sched = np.ascontiguousarray(sched, dtype=np.float64)
     slices = int(slices)
     if not 2 <= slices <= 64:
@@ -146,7 +148,7 @@ def QuantumAnnealReplicas(sched, mcsteps, slices, temp, nspins, spins0, nbs, see
     if energies:
         out["energies"] = d.energy(download=download)
     if download:
-        out["words"] = d.state_download_words()
+        out["words"] = d.state_download_words(out=words_out)
     else:
         d.synchronize()
     return out

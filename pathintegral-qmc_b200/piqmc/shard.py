@@ -1,0 +1,60 @@
+"""Replica sharding across the GPUs of one box (one process per GPU, torch.distributed).
+
+Replicas never interact -- in the reference they are separate calls or separate MPI ranks that
+never communicate (examples/spinglass32_mpi.py:20-26,74-80) -- so the sweep path needs no
+collective: rank g anneals the contiguous block of replicas [replica0, replica0 + count) and
+the Philox key carries the GLOBAL replica id, which makes the result independent of the number of
+ranks.  The only communication is one gather of the final energies (and, optionally, of the
+bit-packed configurations) at the end.
+"""
+import numpy as np
+
+
+def shard_replicas(nreplicas, world_size, rank):
+    """Contiguous shard of `nreplicas` for `rank`: (replica0, count).  The first
+    nreplicas % world_size ranks take one extra replica."""
+    if not 0 <= rank < world_size:
+        raise ValueError("rank out of range")
+    base, extra = divmod(int(nreplicas), int(world_size))
+    count = base + (1 if rank < extra else 0)
+    replica0 = rank * base + min(rank, extra)
+    return replica0, count
+
+
+def gather_rows(local, nreplicas, group=None):
+    """All-gather a per-replica tensor (first dimension = this rank's replicas, sharded with
+    shard_replicas) into the full [nreplicas, ...] tensor, in global replica order, on every
+    rank.  Works on CUDA tensors (NCCL) and CPU tensors (gloo); uneven shards are padded."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    counts = [shard_replicas(nreplicas, world, r)[1] for r in range(world)]
+    cmax = max(counts)
+    if local.shape[0] != counts[dist.get_rank(group)]:
+        raise ValueError("local tensor does not match this rank's shard")
+    pad = torch.zeros((cmax,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    out = torch.empty((world, cmax) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out.view((world * cmax,) + tuple(local.shape[1:])), pad, group=group)
+    return torch.cat([out[r, :counts[r]] for r in range(world)], dim=0)
+
+
+def gather_energies(dev, nreplicas, group=None):
+    """Final-energy gather for a Device whose resident rows are this rank's replica shard:
+    runs the device energy reduction and all-gathers float64[nreplicas, lanes] over NCCL without
+    staging through the host."""
+    import torch
+    dev.energy(download=False)
+    dev.synchronize()
+    local = torch.as_tensor(dev.energy_device_array(), device="cuda:%d" % dev.index)
+    return gather_rows(local, nreplicas, group)
+
+
+def gather_words(dev, nreplicas, group=None):
+    """Gather of the bit-packed final configurations: uint64[nreplicas, nspins] on every rank."""
+    import torch
+    dev.synchronize()
+    # device layout is [nspins, nrows]; gather along replicas needs [nrows, nspins].  NCCL has no
+    # uint64: reinterpret as int64.
+    local = torch.as_tensor(dev.state_device_array(), device="cuda:%d" % dev.index).view(torch.int64)
+    return gather_rows(local.t().contiguous(), nreplicas, group)
