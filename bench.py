@@ -36,6 +36,10 @@ GAMMA0, GAMMA1 = 1.5, 1e-8
 SEED = 2024
 B_ALG_HBM = 0.25        # bytes/attempt: each 64-slice word read once + written once per sweep
 B_ALG_SMEM = 1.0        # bytes/attempt touched on chip: own r+w, 4 neighbours, 2 Trotter bits
+# from the ncu captures under profiles/: DRAM bytes moved per sweep of this workload (read + write,
+# = the packed state once each way) and ALU-pipe (LOP3/SHF/IADD class) warp-instructions per attempt
+NCU_DRAM_BYTES_PER_SWEEP = 4.33e9
+NCU_ALU_WINST_PER_ATTEMPT = 0.205
 METRIC = "spin-flip attempts/sec"
 
 
@@ -178,7 +182,7 @@ def run_reference(args):
 def config_dict(args, cores_note=None):
     c = {"workload": "synthetic 256x256 Gaussian 2D Ising torus, P=64 slices, R=4096 replicas total, "
                      "T=0.01, Gamma 1.5->1e-8 over K steps, mcsteps=1 (BASELINE.json configs[4])",
-         "nspins": L * L, "slices": P, "replicas_total": R_TOTAL, "order": args.order,
+         "nspins": L * L, "slices": P, "replicas_total": args.replicas, "order": args.order,
          "state": "bit-packed uint64 word per (spin, replica), 2.1 GB total",
          "l2_policy": "inputs larger than L2: per-GPU state %.0f MB >> 126 MB L2 at N<=8" % (R_TOTAL * L * L * 8 / 1e6 / 8)}
     if cores_note:
@@ -299,10 +303,17 @@ def run_ours(args):
                 "d2h_bytes_per_step": d2h / K, "seconds": e2e_s},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": "colour_sweep", "achieved": achieved, "peak": pk["hbm_gbs"],
-                     "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": None,
+                     "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
+                     "traffic": NCU_DRAM_BYTES_PER_SWEEP * K / launches / world,
                      "peak_source": pk_kind, "bytes_per_attempt": B_ALG_HBM,
-                     "note": "issue-bound kernel (~tens of instructions per attempt, no contraction); "
-                             "HBM fraction is low by construction, see DESIGN.md section 4"},
+                     "note": "ALU-pipe-bound kernel (~6 logic instructions per attempt, no contraction): the HBM "
+                             "fraction is low by construction, traffic (ncu, bytes per launch) equals the "
+                             "algorithmic bytes; see roofline_alu and DESIGN.md section 4"},
+        "roofline_alu": {"bound": "alu_pipe", "achieved": NCU_ALU_WINST_PER_ATTEMPT * value / world / 1e9,
+                         "peak": nsm * 4 * 0.5 * sm_mhz * 1e6 / 1e9, "unit": "G warp-inst/s",
+                         "frac": NCU_ALU_WINST_PER_ATTEMPT * value / world / (nsm * 4 * 0.5 * sm_mhz * 1e6),
+                         "peak_source": "%d SMs x 4 SMSP x 0.5 warp-inst/clk (integer/logic pipe) x %.0f MHz" % (nsm, sm_mhz),
+                         "alu_warp_inst_per_attempt": NCU_ALU_WINST_PER_ATTEMPT},
         "roofline_smem": {"achieved": B_ALG_SMEM * value / world / 1e9, "peak": smem_peak, "unit": "GB/s",
                           "frac": B_ALG_SMEM * value / world / 1e9 / smem_peak,
                           "bytes_per_attempt": B_ALG_SMEM, "peak_source": "128 B/clk/SM x %d SMs x %.0f MHz" % (nsm, sm_mhz)},
@@ -334,7 +345,9 @@ def main():
     ap.add_argument("--order", default="natural", choices=["natural", "checkerboard"])
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--replicas", type=int, default=4096, help="total replicas over all ranks (default 4096)")
     args = ap.parse_args()
+    globals()["R_TOTAL"] = args.replicas
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -623,6 +623,11 @@ int piqmc_state_alloc(piqmc_handle h, int nrows, int lanes)
     PIQMC_REQUIRE(nrows > 0 && nrows <= 65535, PIQMC_EINVAL, "nrows must be in [1, 65535]");
     PIQMC_REQUIRE(lanes >= 1 && lanes <= 64, PIQMC_EINVAL,
                   "lanes must be in [1, 64] (the packed path holds all slices of a spin in one 64-bit word)");
+    if (h->d_words && h->nrows == nrows && h->lanes == lanes) {
+        // same shape: keep the buffers (and the dataflow flags, which are consistent between runs)
+        PIQMC_CUDA(cudaMemsetAsync(h->d_words, 0, (size_t)nrows * h->nspins * sizeof(uint64_t), h->stream));
+        return PIQMC_OK;
+    }
     PIQMC_CUDA(cudaStreamSynchronize(h->stream));
     free_state(h);
     PIQMC_CUDA(cudaMalloc(&h->d_words, (size_t)nrows * h->nspins * sizeof(uint64_t)));

@@ -19,6 +19,8 @@
 // in algebraic normal form; (3) the few words with lanes that need a uniform are resolved
 // cooperatively by the warp (one Philox block per thread).  Semantics: oracle_qa_colour /
 // oracle_sa_colour (oracle/piqmc_oracle.c part 3), bit for bit.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -232,6 +234,7 @@ struct FastArgs {
     int per_sweep_lists;        // members/level advance by N per sweep
     uint32_t k0, k1, row0, sweep0, tag0;
     unsigned int ticket_base;   // units handed out by earlier launches of the same run
+    unsigned int poll_ns;       // back-off between polls of a completion flag (0 = spin)
 };
 
 template <bool QA>
@@ -277,7 +280,8 @@ __global__ void __launch_bounds__(FAST_THREADS, 5) colour_sweep_fast(const FastA
             }
             if (must) {
                 const uint32_t *flag = a.done + (size_t)j * a.nchunks + chunk;
-                while ((int32_t)(ld_acquire(flag) - want) < 0) __nanosleep(32);
+                while ((int32_t)(ld_acquire(flag) - want) < 0)
+                    if (a.poll_ns) __nanosleep(a.poll_ns);
             }
         }
     }
@@ -309,8 +313,8 @@ __global__ void __launch_bounds__(FAST_THREADS, 5) colour_sweep_fast(const FastA
         const uint64_t w = w_nx;
         uint64_t x[4];
 #pragma unroll
-        for (int n = 0; n < 4; n++)          // self entries (local fields): x = w; unused columns: 0
-            x[n] = (live && n < maxnb) ? ((nb[n] == i) ? w : (w ^ wn_nx[n])) : 0ull;
+        for (int n = 0; n < 4; n++)          // self entries (local fields) were not loaded: x = w ^ 0;
+            x[n] = w ^ wn_nx[n];             // unused columns: any x does (the tables ignore that bit)
         {
             const int rown = row + FAST_THREADS;
             w_nx = 0;
@@ -407,6 +411,10 @@ int launch_fast_sweeps(piqmc_ctx *c, int qa, int nsweeps, const int32_t *d_membe
     // overhead, but fewer independent chunks; keep >= 8 chunks when the state allows
     int rpb = 512;
     while (rpb > FAST_THREADS && (c->nrows + rpb - 1) / rpb < 8) rpb >>= 1;
+    if (const char *e = getenv("PIQMC_ROWS_PER_BLOCK")) {          // tuning knob
+        const int v = atoi(e);
+        if (v >= FAST_THREADS && v % FAST_THREADS == 0) rpb = v;
+    }
     const int nchunks = (c->nrows + rpb - 1) / rpb;
     const size_t nflags = (size_t)c->nspins * nchunks;
     if (c->flow_nchunks != nchunks || c->d_done == nullptr) {
@@ -439,6 +447,8 @@ int launch_fast_sweeps(piqmc_ctx *c, int qa, int nsweeps, const int32_t *d_membe
     a.k0 = (uint32_t)seed;
     a.k1 = (uint32_t)(seed >> 32);
     a.row0 = row0;
+    a.poll_ns = 0;
+    if (const char *e = getenv("PIQMC_POLL_NS")) a.poll_ns = (unsigned int)atoi(e);
 
     const size_t per_sweep = nflags;
     const int max_sweeps = (int)std::max<size_t>(1, ((size_t)1 << 30) / per_sweep);

@@ -2,9 +2,10 @@
 //
 //   E = - sum_{bonds} J_ij s_i s_j - sum_i J_ii s_i          (float64)
 //
-// Packed path: the ELL table lists every bond in both endpoint rows (tools.pyx:84-92), so the
-// quadratic part is accumulated over all table entries and halved; diagonal entries appear once
-// as self-neighbours.  Summation order is fixed (no atomics): results are reproducible.
+// Packed path: the ELL table of tools.GenerateNeighbors lists every stored key (a, b) in both
+// endpoint rows (tools.pyx:84-92), so each key is counted once by keeping only the entries whose
+// neighbour index is larger than the row index; diagonal keys appear once as self-neighbours.
+// Summation order is fixed (no atomics): results are reproducible.
 #include "common.cuh"
 
 namespace {
@@ -25,6 +26,7 @@ __global__ void __launch_bounds__(64 * EN_CHUNKS) energy_partial_kernel(
         const uint64_t w = wrow[(size_t)i * nrows];
         for (int n = 0; n < maxnb; n++) {
             const int j = idx[(size_t)i * maxnb + n];
+            if (j < i) continue;                              // the key is counted in row j
             const double jv = J[(size_t)i * maxnb + n];
             if (j == i) {
                 el += ((w >> lane) & 1) ? -jv : jv;
@@ -63,7 +65,7 @@ __global__ void energy_final_kernel(const double *__restrict__ part, int nblocks
         q += p[lane];
         l += p[64 + lane];
     }
-    out[tid] = -0.5 * q - l;
+    out[tid] = -q - l;
 }
 
 // COO path for host configurations (drop-in ClassicalIsingEnergy): one block per configuration.
