@@ -327,8 +327,30 @@ __global__ void __launch_bounds__(FAST_THREADS, 5) colour_sweep_fast(const FastA
         }
         const uint32_t prow_warp = a.row0 + (uint32_t)(base + (threadIdx.x & ~31));
 
-        // ---- the 2*NC boolean functions of the neighbour pattern, all 64 lanes at once (ANF)
-        uint64_t Fa[NC], Fn[NC];
+        // ---- Trotter disagreement masks.  Reference neighbours: slices P-1 (old value for everyone;
+        //      itself for lane P-1) and 1 (old for lane 0, itself for lane 1, new for lanes >= 2):
+        //      lane 1 is decided first, straight from the truth tables.
+        uint64_t XL = 0, XR = 0, flips = 0, todo = live ? valid : 0ull;
+        if (QA) {
+            const uint64_t bl = ((w >> (lanes - 1)) & 1ull) ? ~0ull : 0ull;
+            const uint64_t br_old = ((w >> 1) & 1ull) ? ~0ull : 0ull;
+            XL = (w ^ bl) & ~(1ull << (lanes - 1));
+            const uint32_t c1 = (uint32_t)(XL >> 1) & 1u;               // right neighbour of lane 1 is itself
+            const uint32_t p1 = pattern_at(x, 1);
+            if (live) {
+                if ((tab.hacc[c1] >> p1) & 1u) flips = 2ull;
+                else if ((tab.hneed[c1] >> p1) & 1u)                     // ~1% of the words
+                    if (lane_uniform(1, (uint32_t)i, sweep, a.row0 + (uint32_t)row, a.k0, a.k1) < tab.thr[c1][p1])
+                        flips = 2ull;
+            }
+            const uint64_t br_new = br_old ^ (flips ? ~0ull : 0ull);
+            XR = ((w ^ br_new) & ~1ull) | ((w ^ br_old) & 1ull);       // lane 0 sees the old bit 1
+            todo &= ~2ull;
+        }
+
+        // ---- "accept by sign" and "needs a uniform" for all 64 lanes at once: per Trotter class a
+        //      4-input boolean function of the disagreement masks, evaluated in algebraic normal form
+        uint64_t ACC = 0, NEED = 0;
         {
             uint32_t mlo[16], mhi[16];
             mlo[0] = mhi[0] = 0xFFFFFFFFu;
@@ -343,47 +365,33 @@ __global__ void __launch_bounds__(FAST_THREADS, 5) colour_sweep_fast(const FastA
             }
 #pragma unroll
             for (int c = 0; c < NC; c++) {
-                uint32_t alo = tab.cacc[c][0], ahi = alo, nlo = tab.cneed[c][0], nhi = nlo;
+                // lanes of Trotter class c
+                const uint64_t Cc = !QA ? ~0ull : (c == 0 ? ~(XL | XR) : (c == 1 ? (XL ^ XR) : (XL & XR)));
+                const uint32_t clo = (uint32_t)Cc, chi = (uint32_t)(Cc >> 32);
+                uint32_t alo = tab.cacc[c][0], ahi = alo;
 #pragma unroll
                 for (int S = 1; S < 16; S++) {
-                    const uint32_t ca = tab.cacc[c][S], cn = tab.cneed[c][S];
+                    const uint32_t ca = tab.cacc[c][S];
                     alo ^= ca & mlo[S];
                     ahi ^= ca & mhi[S];
-                    nlo ^= cn & mlo[S];
-                    nhi ^= cn & mhi[S];
                 }
-                Fa[c] = ((uint64_t)ahi << 32) | alo;
-                Fn[c] = ((uint64_t)nhi << 32) | nlo;
+                ACC |= ((uint64_t)(ahi & chi) << 32) | (alo & clo);
+                // no pattern of this class needs a uniform for ~70% of (spin, class) pairs at T << J:
+                // block-uniform skip
+                if (tab.hneed[c] != 0u) {
+                    uint32_t nlo = tab.cneed[c][0], nhi = nlo;
+#pragma unroll
+                    for (int S = 1; S < 16; S++) {
+                        const uint32_t cn = tab.cneed[c][S];
+                        nlo ^= cn & mlo[S];
+                        nhi ^= cn & mhi[S];
+                    }
+                    NEED |= ((uint64_t)(nhi & chi) << 32) | (nlo & clo);
+                }
             }
         }
-
-        uint64_t ACC, NEED, XL = 0, XR = 0, flips = 0;
-        if (QA) {
-            // reference Trotter neighbours: slices P-1 (old value for everyone; itself for lane P-1)
-            // and 1 (old for lane 0, itself for lane 1, new for lanes >= 2): decide lane 1 first.
-            const uint64_t bl = ((w >> (lanes - 1)) & 1ull) ? ~0ull : 0ull;
-            const uint64_t br_old = ((w >> 1) & 1ull) ? ~0ull : 0ull;
-            XL = (w ^ bl) & ~(1ull << (lanes - 1));
-            {
-                const uint32_t c1 = (uint32_t)(XL >> 1) & 1u;           // lane 1: right neighbour is itself
-                const uint64_t one = live ? 2ull : 0ull;
-                flips = (c1 ? Fa[1] : Fa[0]) & one;
-                if ((c1 ? Fn[1] : Fn[0]) & one)                          // ~1% of the words
-                    if (lane_uniform(1, (uint32_t)i, sweep, a.row0 + (uint32_t)row, a.k0, a.k1) <
-                        tab.thr[c1][pattern_at(x, 1)])
-                        flips = 2ull;
-            }
-            const uint64_t br_new = br_old ^ ((flips & 2ull) ? ~0ull : 0ull);
-            XR = ((w ^ br_new) & ~1ull) | ((w ^ br_old) & 1ull);       // lane 0 sees the old bit 1
-            const uint64_t todo = live ? (valid & ~2ull) : 0ull;
-            const uint64_t C0 = ~(XL | XR), C1 = XL ^ XR, C2 = XL & XR;
-            ACC = ((C0 & Fa[0]) | (C1 & Fa[1]) | (C2 & Fa[NC - 1])) & todo;
-            NEED = ((C0 & Fn[0]) | (C1 & Fn[1]) | (C2 & Fn[NC - 1])) & todo;
-        } else {
-            const uint64_t todo = live ? valid : 0ull;
-            ACC = Fa[0] & todo;
-            NEED = Fn[0] & todo;
-        }
+        ACC &= todo;
+        NEED &= todo;
         if (__any_sync(0xffffffffu, NEED != 0))
             ACC |= resolve_draws<QA>(NEED, x, XL, XR, tab, queue, (uint32_t)i, sweep, prow_warp, a.k0, a.k1);
         if (live) wrow[(size_t)i * nrows] = w ^ flips ^ ACC;

@@ -307,7 +307,58 @@ def make_distributions(nrep=1024):
     np.savez_compressed(os.path.join(HERE, "ref_distributions.npz"), **out)
 
 
+def make_config4(nsamples=4096):
+    """BASELINE configs[3]: bipartite8 (examples/bipartite8.py:20-27,60-66) and hopfield8
+    (examples/hopfield8.py:22-45,98) annealed with the reference's sa.Anneal and
+    sa.Anneal_multispin from random starts; stored: final state index (8 bits, bit i = spin i down)
+    and final energy of every sample."""
+    ref = O.ref()
+    from piqmc_ref import sa, tools
+    inst = instances()
+    out = {}
+    cfgs = {"bipartite8": (np.linspace(3.0, 0.01, 10), 1), "hopfield8": (8.0 * (1e-8 / 8.0) ** (np.arange(5) / 5.0), 100)}
+    for name, (sched, mcsteps) in cfgs.items():
+        ijv, n = inst[name]
+        J = dok_from_ijv(ijv, n)
+        nbs = np.asarray(tools.GenerateNeighbors(n, J, MAXNB[name]))
+        out["sched_" + name] = sched
+        out["mcsteps_" + name] = np.array(mcsteps)
+        rng = np.random.RandomState(4)
+        libc.srand(4)
+        states, en = [], []
+        for _ in range(nsamples):
+            sv = np.array([2 * rng.randint(2) - 1 for _ in range(n)], dtype=np.float64)
+            sa.Anneal(sched, mcsteps, sv, nbs, rng)
+            states.append(int(np.sum((sv < 0) * (1 << np.arange(n)))))
+            en.append(sa.ClassicalIsingEnergy(sv, J))
+        out["sa_state_" + name] = np.array(states, dtype=np.int32)
+        out["sa_energy_" + name] = np.array(en)
+        states, en = [], []
+        rng = np.random.RandomState(5)
+        for _ in range(nsamples // 64):
+            buf = np.zeros((65, n))
+            bits = buf[:64]
+            bits[:] = rng.randint(2, size=(64, n))
+            sa.Anneal_multispin(sched, mcsteps, bits, nbs, rng)
+            # column 0 of rows 1..63 is corrupted by the reference's unpack overrun: use row 0 only
+            # for spin 0 ... instead keep all rows but mark spin 0 as unknown for rows >= 1
+            for k in range(64):
+                sv = 1.0 - 2.0 * bits[k]
+                if k > 0:
+                    continue
+                states.append(int(np.sum((sv < 0) * (1 << np.arange(n)))))
+                en.append(sa.ClassicalIsingEnergy(sv, J))
+        out["ms_state_" + name] = np.array(states, dtype=np.int32)
+        out["ms_energy_" + name] = np.array(en)
+        print(name, "sa mean E", np.mean(out["sa_energy_" + name]), "multispin(row 0) mean E", np.mean(en))
+    np.savez_compressed(os.path.join(HERE, "ref_config4.npz"), **out)
+
+
 if __name__ == "__main__":
+    if "--config4" in sys.argv:
+        make_config4()
+        sys.exit(0)
     make_vectors()
     if "--dist" in sys.argv:
         make_distributions()
+        make_config4()

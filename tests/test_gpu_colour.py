@@ -269,3 +269,32 @@ def test_sa_colour_residual_energy_distribution_vs_reference(golden, dev, nsteps
     print("nsteps", nsteps, "residual/spin mine %.4f ref %.4f KS p %.3f"
           % (_residual(out["energies"].mean(), "inst_0_32x32"), _residual(ref.mean(), "inst_0_32x32"), p))
     assert p > 0.01
+
+
+# ------------------------------------------------------------------------------------ config 4
+@pytest.mark.parametrize("inst", ["bipartite8", "hopfield8"])
+def test_config4_state_populations_vs_reference(golden, dev, inst):
+    """BASELINE configs[3]: bipartite8 / hopfield8 through the multispin-coded SA kernel (64
+    replicas per word).  Final-state populations over the 2^8 states and final energies of 4096
+    replicas against 4096 runs of the reference's sa.Anneal (golden): chi-square on the state
+    histogram (rare states pooled) and KS on the energies, p > 0.01."""
+    import os
+    from scipy.stats import chi2_contingency
+    import piqmc.sa as sa
+    g4 = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_config4.npz"))
+    nbs = golden["vec"]["nbs_" + inst]
+    sched, mcsteps = g4["sched_" + inst], int(g4["mcsteps_" + inst])
+    ref_state, ref_en = g4["sa_state_" + inst], g4["sa_energy_" + inst]
+    R = ref_state.size
+    out = sa.AnnealReplicas(sched, mcsteps, None, nbs, seed=404, order="permutation", nreplicas=R, device=dev)
+    mine_state = ((out["spins"] < 0) * (1 << np.arange(8))).sum(axis=1)
+    a = np.bincount(mine_state, minlength=256).astype(float)
+    b = np.bincount(ref_state, minlength=256).astype(float)
+    big = (a + b) >= 20
+    table = np.array([np.append(a[big], a[~big].sum()), np.append(b[big], b[~big].sum())])
+    table = table[:, table.sum(axis=0) > 0]
+    p_chi = chi2_contingency(table)[1]
+    p_ks = ks_2samp_p(out["energies"], ref_en)
+    print(inst, "states used", int(big.sum()), "chi2 p %.3f  KS(energy) p %.3f  mean E mine %.3f ref %.3f"
+          % (p_chi, p_ks, out["energies"].mean(), ref_en.mean()))
+    assert p_chi > 0.01 and p_ks > 0.01
