@@ -300,7 +300,7 @@ def run_ours(args):
         "dtype": "f32", "data": "synthetic", "config": config_dict(args),
         "clocks": clocks,
         "e2e": {"value": attempts / e2e_s, "unit": "attempts/s", "h2d_bytes_per_step": h2d / K,
-                "d2h_bytes_per_step": d2h / K, "seconds": e2e_s},
+                "d2h_bytes_per_step": d2h / K, "seconds": e2e_s, "breakdown_s": out["seconds"]},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": "colour_sweep", "achieved": achieved, "peak": pk["hbm_gbs"],
                      "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],

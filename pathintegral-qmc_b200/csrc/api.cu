@@ -46,6 +46,8 @@ void free_graph(piqmc_ctx *c)
     free_dev(c->d_J32_t);
     free_dev(c->d_members);
     free_dev(c->d_level);
+    free_dev(c->d_pmembers);
+    free_dev(c->d_psweepoff);
     free_dev(c->d_done);
     c->flow_nchunks = 0;
     c->color_off.clear();
@@ -131,6 +133,26 @@ static int apply_colouring(piqmc_ctx *h, int ncolors, const int32_t *color, bool
     PIQMC_CUDA(cudaMemcpy(h->d_members, members.data(), (size_t)h->nspins * sizeof(int32_t),
                           cudaMemcpyHostToDevice));
     PIQMC_CUDA(cudaMemcpy(h->d_level, color, (size_t)h->nspins * sizeof(int32_t), cudaMemcpyHostToDevice));
+    // period-major order for the dataflow kernel: D = 1 + largest level gap across a coupled pair
+    int D = 1;
+    for (int i = 0; i < h->nspins; i++)
+        for (int n = 0; n < h->maxnb; n++) {
+            const size_t e = (size_t)i * h->maxnb + n;
+            if (h->h_live[e]) D = std::max(D, std::abs(color[i] - color[h->h_idx[e]]) + 1);
+        }
+    std::vector<int32_t> order(h->nspins), pm(h->nspins), po(h->nspins);
+    for (int i = 0; i < h->nspins; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+        const int rx = color[x] % D, ry = color[y] % D;
+        return rx != ry ? rx < ry : color[x] < color[y];
+    });
+    for (int k = 0; k < h->nspins; k++) {
+        pm[k] = order[k];
+        po[k] = color[order[k]] / D;
+    }
+    PIQMC_CUDA(cudaMemcpy(h->d_pmembers, pm.data(), (size_t)h->nspins * sizeof(int32_t), cudaMemcpyHostToDevice));
+    PIQMC_CUDA(cudaMemcpy(h->d_psweepoff, po.data(), (size_t)h->nspins * sizeof(int32_t), cudaMemcpyHostToDevice));
+    h->flow_extra = (ncolors + D - 1) / D - 1;
     h->ncolors = ncolors;
     return PIQMC_OK;
 }
@@ -201,8 +223,8 @@ static int run_colour_sweeps(piqmc_ctx *h, int qa, int trotter, int nsched, int 
 
     if (!orders) {
         if (fast) {
-            TRY(launch_fast_sweeps(h, qa, (int)nsweeps, h->d_members, h->d_level, 0, d_jp2.p, d_invT.p, seed,
-                                   row0, sweep0));
+            TRY(launch_fast_sweeps(h, qa, (int)nsweeps, h->d_pmembers, h->d_level, h->d_psweepoff, h->flow_extra, 0,
+                                   d_jp2.p, d_invT.p, seed, row0, sweep0));
             // the per-sweep parameter arrays must outlive the launch
             PIQMC_CUDA(cudaStreamSynchronize(h->stream));
             return PIQMC_OK;
@@ -239,8 +261,8 @@ static int run_colour_sweeps(piqmc_ctx *h, int qa, int trotter, int nsched, int 
         if (fast) {
             PIQMC_CUDA(cudaMemcpyAsync(d_lev.p, levels.data(), m * N * sizeof(int32_t), cudaMemcpyHostToDevice,
                                        h->stream));
-            TRY(launch_fast_sweeps(h, qa, (int)m, d_mem.p, d_lev.p, 1, d_jp2.p + base, d_invT.p + base, seed, row0,
-                                   sweep0 + (uint32_t)base));
+            TRY(launch_fast_sweeps(h, qa, (int)m, d_mem.p, d_lev.p, nullptr, 0, 1, d_jp2.p + base, d_invT.p + base,
+                                   seed, row0, sweep0 + (uint32_t)base));
         } else {
             for (size_t s = 0; s < m; s++) {
                 const int f = (int)((base + s) / mcsteps);
@@ -302,6 +324,7 @@ int piqmc_destroy(piqmc_handle h)
     free_state(h);
     free_dev(h->d_epart);
     free_dev(h->d_ticket);
+    free_dev(h->d_stage);
     cudaStreamDestroy(h->stream);
     delete h;
     return PIQMC_OK;
@@ -447,6 +470,8 @@ int piqmc_set_graph(piqmc_handle h, int nspins, int maxnb, const int32_t *idx, c
         }
     PIQMC_CUDA(cudaMalloc(&h->d_members, (size_t)nspins * sizeof(int32_t)));
     PIQMC_CUDA(cudaMalloc(&h->d_level, (size_t)nspins * sizeof(int32_t)));
+    PIQMC_CUDA(cudaMalloc(&h->d_pmembers, (size_t)nspins * sizeof(int32_t)));
+    PIQMC_CUDA(cudaMalloc(&h->d_psweepoff, (size_t)nspins * sizeof(int32_t)));
     if (color) TRY(apply_colouring(h, ncolors, color, false));
     // a new graph invalidates any resident state
     free_state(h);
@@ -651,10 +676,15 @@ int piqmc_state_upload_spins(piqmc_handle h, const int8_t *spins, int tile)
     PIQMC_REQUIRE(h->d_words, PIQMC_ENOSTATE, "no packed state (call piqmc_state_alloc)");
     PIQMC_REQUIRE(spins, PIQMC_EINVAL, "null spins");
     const size_t n = (size_t)h->nrows * h->nspins * (tile ? 1 : h->lanes);
-    DevBuf<int8_t> d;
-    PIQMC_CUDA(d.alloc(n));
-    PIQMC_CUDA(cudaMemcpyAsync(d.p, spins, n, cudaMemcpyHostToDevice, h->stream));
-    TRY(launch_pack_spins(h, d.p, tile));
+    if (n > h->stage_bytes) {                       // grow-only staging buffer: no malloc/free per call
+        PIQMC_CUDA(cudaStreamSynchronize(h->stream));
+        free_dev(h->d_stage);
+        h->stage_bytes = 0;
+        PIQMC_CUDA(cudaMalloc(&h->d_stage, n));
+        h->stage_bytes = n;
+    }
+    PIQMC_CUDA(cudaMemcpyAsync(h->d_stage, spins, n, cudaMemcpyHostToDevice, h->stream));
+    TRY(launch_pack_spins(h, (const int8_t *)h->d_stage, tile));
     PIQMC_CUDA(cudaStreamSynchronize(h->stream));
     return PIQMC_OK;
 }

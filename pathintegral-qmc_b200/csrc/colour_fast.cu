@@ -227,6 +227,8 @@ struct FastArgs {
     const float *J_t;           // [maxnb][N]
     const int32_t *members;     // per sweep (or shared): spins in level-major order
     const int32_t *level;       // per sweep (or shared): level of every spin
+    const int32_t *sweepoff;    // static colouring only: sweep lag of member m (NULL: none)
+    int nsweeps;                // sweeps covered by this launch
     const float *jp2, *invT;    // per sweep
     uint32_t *done;             // [N][nchunks] tag of the last finished sweep
     unsigned int *ticket;
@@ -248,12 +250,20 @@ __global__ void __launch_bounds__(FAST_THREADS, 5) colour_sweep_fast(const FastA
     if (threadIdx.x == 0) s_ticket = atomicAdd(a.ticket, 1u) - a.ticket_base;
     __syncthreads();
     const unsigned int t = s_ticket;
+    // Tickets run over "periods" of N spins.  With a static colouring the member list is sorted by
+    // (level mod D, level) and sweepoff[m] = level div D, D = 1 + the largest level gap across an
+    // edge: period q then holds level rho of sweep q next to level rho+D of sweep q-1, ..., i.e.
+    // consecutive sweeps overlap as far as the dependencies allow and ticket order is still a
+    // topological order (a unit only waits for smaller tickets).
     const unsigned int per_sweep = (unsigned int)a.nspins * (unsigned int)a.nchunks;
-    const int s = (int)(t / per_sweep);
-    const unsigned int rem = t - (unsigned int)s * per_sweep;
+    const int q = (int)(t / per_sweep);
+    const unsigned int rem = t - (unsigned int)q * per_sweep;
     const int chunk = (int)(rem % (unsigned int)a.nchunks);
+    const unsigned int m = rem / (unsigned int)a.nchunks;
+    const int s = a.sweepoff ? q - a.sweepoff[m] : q;
+    if (s < 0 || s >= a.nsweeps) return;                           // ramp-up / ramp-down periods
     const size_t lbase = a.per_sweep_lists ? (size_t)s * a.nspins : 0;
-    const int i = a.members[lbase + rem / (unsigned int)a.nchunks];
+    const int i = a.members[lbase + m];
     const uint32_t tag = a.tag0 + (uint32_t)s + 1u;
     const uint32_t sweep = a.sweep0 + (uint32_t)s;
     const int nspins = a.nspins, nrows = a.nrows, maxnb = a.maxnb, lanes = a.lanes;
@@ -411,8 +421,8 @@ __global__ void __launch_bounds__(FAST_THREADS, 5) colour_sweep_fast(const FastA
 // members/level: device arrays, level-major spin order and level per spin; either one list for
 // all sweeps or one per sweep.  d_jp2/d_invT: per sweep.
 int launch_fast_sweeps(piqmc_ctx *c, int qa, int nsweeps, const int32_t *d_members, const int32_t *d_level,
-                       int per_sweep_lists, const float *d_jp2, const float *d_invT, uint64_t seed,
-                       uint32_t row0, uint32_t sweep0)
+                       const int32_t *d_sweepoff, int nperiods_extra, int per_sweep_lists, const float *d_jp2,
+                       const float *d_invT, uint64_t seed, uint32_t row0, uint32_t sweep0)
 {
     if (nsweeps <= 0) return PIQMC_OK;
     // rows per block: the per-spin table is built once per block, so more rows per block is less
@@ -459,17 +469,22 @@ int launch_fast_sweeps(piqmc_ctx *c, int qa, int nsweeps, const int32_t *d_membe
     if (const char *e = getenv("PIQMC_POLL_NS")) a.poll_ns = (unsigned int)atoi(e);
 
     const size_t per_sweep = nflags;
-    const int max_sweeps = (int)std::max<size_t>(1, ((size_t)1 << 30) / per_sweep);
+    const int max_sweeps = (int)std::max<long long>(1, (long long)(((size_t)1 << 30) / per_sweep) - nperiods_extra);
+    unsigned int ticket_base = 0;
     for (int s0 = 0; s0 < nsweeps; s0 += max_sweeps) {
         const int ns = std::min(max_sweeps, nsweeps - s0);
         a.members = d_members + (per_sweep_lists ? (size_t)s0 * c->nspins : 0);
         a.level = d_level + (per_sweep_lists ? (size_t)s0 * c->nspins : 0);
+        a.sweepoff = d_sweepoff;
+        a.nsweeps = ns;
         a.jp2 = d_jp2 + s0;
         a.invT = d_invT + s0;
         a.sweep0 = sweep0 + (uint32_t)s0;
         a.tag0 = c->flow_tag + (uint32_t)s0;
-        a.ticket_base = (unsigned int)((size_t)s0 * per_sweep);
-        dim3 block(FAST_THREADS), grid((unsigned)((size_t)ns * per_sweep));
+        a.ticket_base = ticket_base;
+        const size_t nunits = (size_t)(ns + nperiods_extra) * per_sweep;
+        ticket_base += (unsigned int)nunits;
+        dim3 block(FAST_THREADS), grid((unsigned)nunits);
         if (qa) colour_sweep_fast<true><<<grid, block, 0, c->stream>>>(a);
         else    colour_sweep_fast<false><<<grid, block, 0, c->stream>>>(a);
         c->launches++;

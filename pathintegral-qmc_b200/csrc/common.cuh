@@ -52,6 +52,9 @@ struct piqmc_ctx {
     std::vector<int32_t> h_idx;     // host copies for level colourings of per-sweep orders
     std::vector<uint8_t> h_live;    // J != 0 && idx != self
     int32_t *d_level = nullptr;     // colour (level) of every spin (static colouring)
+    int32_t *d_pmembers = nullptr;  // spins sorted by (level mod D, level): period-major order
+    int32_t *d_psweepoff = nullptr; // level div D of those members
+    int flow_extra = 0;             // ceil(ncolors / D) - 1 ramp periods
     // dataflow sweep kernel (colour_fast.cu)
     uint32_t *d_done = nullptr;     // [N][flow_nchunks] tag of the last finished sweep
     unsigned int *d_ticket = nullptr;
@@ -62,6 +65,8 @@ struct piqmc_ctx {
     int nrows = 0, lanes = 0;
     uint64_t *d_words = nullptr;    // [N][nrows]  (row fastest)
     double *d_energy = nullptr;     // [nrows][lanes]
+    void *d_stage = nullptr;        // grow-only staging buffer for host spins
+    size_t stage_bytes = 0;
     double *d_epart = nullptr;      // scratch for the energy reduction
     size_t epart_elems = 0;
 
@@ -137,8 +142,8 @@ int launch_energy_coo(piqmc_ctx *c, int nspins, int nnz, const int32_t *d_row, c
                       const double *d_val, int nconfs, const int8_t *d_spins, double *d_out);
 // the production kernel: nsweeps sweeps in one dataflow launch (colour_fast.cu)
 int launch_fast_sweeps(piqmc_ctx *c, int qa, int nsweeps, const int32_t *d_members, const int32_t *d_level,
-                       int per_sweep_lists, const float *d_jp2, const float *d_invT, uint64_t seed,
-                       uint32_t row0, uint32_t sweep0);
+                       const int32_t *d_sweepoff, int nperiods_extra, int per_sweep_lists, const float *d_jp2,
+                       const float *d_invT, uint64_t seed, uint32_t row0, uint32_t sweep0);
 // variant: 0 auto (fast when graph and state qualify), 1 generic, 2 fast-if-possible
 static inline bool piqmc_fast_ok(const piqmc_ctx *c, int qa, int trotter)
 {

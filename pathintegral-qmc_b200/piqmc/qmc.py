@@ -133,22 +133,30 @@ def QuantumAnnealReplicas(sched, mcsteps, slices, temp, nspins, spins0, nbs, see
     if color is None:
         color, orders = _resolve_order(order, nbs, sched.size * int(mcsteps), int(nspins),
                                        int(seed) & 0xFFFFFFFF)
+    import time
+    t = [time.perf_counter()]
     d.set_graph(nbs, color)
     if int(nspins) != d.nspins:
         raise ValueError("nspins=%d but nbs describes %d spins" % (nspins, d.nspins))
     R = int(nreplicas) if spins0 is None else int(np.asarray(spins0).shape[0])
     d.state_alloc(R, slices)
+    t.append(time.perf_counter())
     if spins0 is None:
         d.state_init_random(seed, replica0, tile=True)
     else:
         d.state_upload_spins(spins0, tile=tile)
+    t.append(time.perf_counter())
     d.qa_colour(sched, int(mcsteps), temp, seed, replica0=replica0, trotter=TROTTER[trotter],
                 orders=orders)
+    t.append(time.perf_counter())
     out = {"energies": None, "words": None}
     if energies:
         out["energies"] = d.energy(download=download)
+    t.append(time.perf_counter())
     if download:
         out["words"] = d.state_download_words(out=words_out)
     else:
         d.synchronize()
+    t.append(time.perf_counter())
+    out["seconds"] = dict(zip(("graph+alloc", "upload", "sweeps", "energy", "download"), np.diff(t).tolist()))
     return out
