@@ -307,6 +307,37 @@ def make_distributions(nrep=1024):
     np.savez_compressed(os.path.join(HERE, "ref_distributions.npz"), **out)
 
 
+def _santoro_init():
+    ref = O.ref()
+    from piqmc_ref import qmc, tools
+    ijv = load_ijv("santoro_80x80")
+    J = dok_from_ijv(ijv, 6400)
+    _G.update(qmc=qmc, J=J.tocsr(), nbs=np.asarray(tools.GenerateNeighbors(6400, J, 4)))
+
+
+def _santoro_job(args):
+    r, nsteps = args
+    N, P, T = 6400, 20, 0.01
+    rng = np.random.RandomState(r)
+    libc.srand(r)
+    sv = np.array([2 * rng.randint(2) - 1 for _ in range(N)], dtype=np.float64)
+    confs = np.tile(sv, (P, 1)).T.copy()
+    _G["qmc"].QuantumAnneal_parallel(np.linspace(1.5, 1e-8, nsteps), 1, P, T, N, confs, _G["nbs"], 1)
+    return _energies(confs)
+
+
+def make_santoro(nrep=256):
+    """Config 3 (examples/santoro80.py:23-33): 80x80, P=20, T=0.01, Gamma 1.5->1e-8 in tau steps,
+    residual energy vs tau with the reference's per-spin-reset variant (nthreads=1)."""
+    out = {}
+    with mp.Pool(min(8, os.cpu_count()), initializer=_santoro_init) as pool:
+        for tau in (10, 30, 100):
+            res = np.array(pool.map(_santoro_job, [(r, tau) for r in range(nrep)], chunksize=4))
+            out["qa_par_%d" % tau] = res
+            print("santoro tau", tau, "mean residual/spin", (res.mean() + 10115.3067314770) / 6400.0)
+    np.savez_compressed(os.path.join(HERE, "ref_santoro.npz"), **out)
+
+
 def make_config4(nsamples=4096):
     """BASELINE configs[3]: bipartite8 (examples/bipartite8.py:20-27,60-66) and hopfield8
     (examples/hopfield8.py:22-45,98) annealed with the reference's sa.Anneal and
@@ -358,7 +389,11 @@ if __name__ == "__main__":
     if "--config4" in sys.argv:
         make_config4()
         sys.exit(0)
+    if "--santoro" in sys.argv:
+        make_santoro()
+        sys.exit(0)
     make_vectors()
     if "--dist" in sys.argv:
         make_distributions()
         make_config4()
+        make_santoro()

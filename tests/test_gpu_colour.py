@@ -298,3 +298,24 @@ def test_config4_state_populations_vs_reference(golden, dev, inst):
     print(inst, "states used", int(big.sum()), "chi2 p %.3f  KS(energy) p %.3f  mean E mine %.3f ref %.3f"
           % (p_chi, p_ks, out["energies"].mean(), ref_en.mean()))
     assert p_chi > 0.01 and p_ks > 0.01
+
+
+# ------------------------------------------------------------------------------------ config 3
+@pytest.mark.parametrize("tau", [10, 30, 100])
+def test_santoro_residual_energy_vs_tau(golden, dev, tau):
+    """BASELINE configs[2] (examples/santoro80.py:23-33): the 80x80 Martonak-Santoro-Tosatti
+    instance, P=20, T=0.01, Gamma 1.5 -> 1e-8 in tau steps; residual energy above the known ground
+    state (examples/ising_instances/santoro_80x80_answer.txt:24).  1024 replicas on the GPU against
+    256 runs of the reference's QuantumAnneal_parallel (golden): KS p > 0.01."""
+    import os
+    import piqmc.qmc as qmc
+    ref = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_santoro.npz"))["qa_par_%d" % tau]
+    nbs = golden["vec"]["nbs_santoro_80x80"]
+    out = qmc.QuantumAnnealReplicas(np.linspace(1.5, 1e-8, tau), 1, 20, 0.01, 6400, None, nbs, seed=8080 + tau,
+                                    order="natural", nreplicas=1024, device=dev)
+    mine = out["energies"]
+    p = ks_2samp_p(_residual(mine.mean(axis=1), "santoro_80x80"), _residual(ref.mean(axis=1), "santoro_80x80"))
+    print("tau", tau, "residual/spin mine %.4f ref %.4f KS p %.3f"
+          % (_residual(mine.mean(), "santoro_80x80"), _residual(ref.mean(), "santoro_80x80"), p))
+    assert p > 0.01
+    assert _residual(mine.min(), "santoro_80x80") > 0.0          # never below the exact ground state
