@@ -144,8 +144,10 @@ int launch_energy_coo(piqmc_ctx *c, int nspins, int nnz, const int32_t *d_row, c
 int launch_fast_sweeps(piqmc_ctx *c, int qa, int nsweeps, const int32_t *d_members, const int32_t *d_level,
                        const int32_t *d_sweepoff, int nperiods_extra, int per_sweep_lists, const float *d_jp2,
                        const float *d_invT, uint64_t seed, uint32_t row0, uint32_t sweep0);
-// variant: 0 auto (fast when graph and state qualify), 1 generic, 2 fast-if-possible
+// variant: 0 auto (fast kernel when the graph qualifies and there are enough rows to fill its
+// 128-thread blocks), 1 generic, 2 fast whenever the graph qualifies (used by the parity tests)
 static inline bool piqmc_fast_ok(const piqmc_ctx *c, int qa, int trotter)
 {
-    return c->variant != 1 && c->maxnb <= 4 && c->nrows >= 32 && (!qa || trotter == 0);
+    if (c->variant == 1 || c->maxnb > 4 || (qa && trotter != 0)) return false;
+    return c->variant == 2 || c->nrows >= 32;
 }

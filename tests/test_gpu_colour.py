@@ -319,3 +319,57 @@ def test_santoro_residual_energy_vs_tau(golden, dev, tau):
           % (_residual(mine.mean(), "santoro_80x80"), _residual(ref.mean(), "santoro_80x80"), p))
     assert p > 0.01
     assert _residual(mine.min(), "santoro_80x80") > 0.0          # never below the exact ground state
+
+
+# ------------------------------------------------------------------- fast kernel, larger states
+@pytest.mark.parametrize("order", ["natural", "checkerboard", "permutation"])
+@pytest.mark.parametrize("R,P", [(300, 8), (130, 64), (33, 20)])
+def test_fast_kernel_many_rows_bit_exact(dev, order, R, P):
+    """The dataflow kernel with several row chunks / several passes per block, non-multiple-of-32
+    row counts and all three visiting orders, against the sequential CPU statement."""
+    import piqmc.qmc as qmc
+    import piqmc.tools as T
+    nbs, idx, J32, checker = _torus(8, 11)
+    n = 64
+    sched = np.linspace(1.5, 1e-8, 6)
+    seed = 1000 + R + P
+    init = O.colour_init_spins(seed, 5, R, n)
+    want = np.repeat(init[:, :, None], P, axis=2).copy()
+    if order == "checkerboard":
+        O.qa_colour(sched, 2, P, 0.03, idx, J32, checker, want, seed, replica0=5, sweep0=3)
+        kw = dict(color=checker)
+    elif order == "natural":
+        O.qa_colour(sched, 2, P, 0.03, idx, J32, checker, want, seed, replica0=5, sweep0=3,
+                    orders=np.tile(np.arange(n, dtype=np.int32), (12, 1)))
+        kw = dict(color=T.ColourGraph(nbs, "natural"))
+    else:
+        prng = np.random.RandomState(R)
+        orders = np.stack([prng.permutation(n) for _ in range(12)]).astype(np.int32)
+        O.qa_colour(sched, 2, P, 0.03, idx, J32, checker, want, seed, replica0=5, sweep0=3, orders=orders)
+        kw = dict(order=orders)
+    dev.set_variant(2)
+    if "color" in kw:
+        dev.set_graph(nbs, kw["color"])
+    else:
+        dev.set_graph(nbs, checker)
+    dev.state_alloc(R, P)
+    dev.state_init_random(seed, 5, tile=True)
+    dev.qa_colour(sched, 2, 0.03, seed, replica0=5, sweep0=3, orders=kw.get("order"))
+    got = np.transpose(T.UnpackWords(dev.state_download_words(), P), (0, 2, 1))
+    dev.set_variant(0)
+    assert np.array_equal(want, got)
+
+
+def test_fast_kernel_sa_many_rows_bit_exact(golden, dev):
+    """SA through the dataflow kernel with 40 rows (2560 replicas), hot and cold temperatures."""
+    import piqmc.sa as sa
+    nbs, idx, J32, color = _torus(8, 12)
+    R, n = 2560, 64
+    rng = np.random.RandomState(1)
+    init = (2 * rng.randint(2, size=(R, n)) - 1).astype(np.int8)
+    for sch in ((3.0, 0.5, 4), (0.3, 0.01, 4)):
+        sched = np.linspace(*sch[:2], sch[2])
+        want = init.copy()
+        O.sa_colour(sched, 2, idx, J32, color, want, seed=77, row0=9)
+        out = sa.AnnealReplicas(sched, 2, init, nbs, 77, color=color, row0=9, device=dev)
+        assert np.array_equal(out["spins"], want)
