@@ -223,7 +223,7 @@ static int run_colour_sweeps(piqmc_ctx *h, int qa, int trotter, int nsched, int 
 
     if (!orders) {
         if (fast) {
-            TRY(launch_fast_sweeps(h, qa, (int)nsweeps, h->d_pmembers, h->d_level, h->d_psweepoff, h->flow_extra, 0,
+            TRY(launch_fast_sweeps(h, qa, trotter, (int)nsweeps, h->d_pmembers, h->d_level, h->d_psweepoff, h->flow_extra, 0,
                                    d_jp2.p, d_invT.p, seed, row0, sweep0));
             // the per-sweep parameter arrays must outlive the launch
             PIQMC_CUDA(cudaStreamSynchronize(h->stream));
@@ -261,7 +261,7 @@ static int run_colour_sweeps(piqmc_ctx *h, int qa, int trotter, int nsched, int 
         if (fast) {
             PIQMC_CUDA(cudaMemcpyAsync(d_lev.p, levels.data(), m * N * sizeof(int32_t), cudaMemcpyHostToDevice,
                                        h->stream));
-            TRY(launch_fast_sweeps(h, qa, (int)m, d_mem.p, d_lev.p, nullptr, 0, 1, d_jp2.p + base, d_invT.p + base,
+            TRY(launch_fast_sweeps(h, qa, trotter, (int)m, d_mem.p, d_lev.p, nullptr, 0, 1, d_jp2.p + base, d_invT.p + base,
                                    seed, row0, sweep0 + (uint32_t)base));
         } else {
             for (size_t s = 0; s < m; s++) {

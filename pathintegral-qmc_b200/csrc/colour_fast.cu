@@ -239,7 +239,7 @@ struct FastArgs {
     unsigned int poll_ns;       // back-off between polls of a completion flag (0 = spin)
 };
 
-template <bool QA>
+template <bool QA, int TROT>
 __global__ void __launch_bounds__(FAST_THREADS, 5) colour_sweep_fast(const FastArgs a)
 {
     __shared__ SpinTable tab;
@@ -337,14 +337,60 @@ __global__ void __launch_bounds__(FAST_THREADS, 5) colour_sweep_fast(const FastA
         }
         const uint32_t prow_warp = a.row0 + (uint32_t)(base + (threadIdx.x & ~31));
 
-        // ---- Trotter disagreement masks.  Reference neighbours: slices P-1 (old value for everyone;
-        //      itself for lane P-1) and 1 (old for lane 0, itself for lane 1, new for lanes >= 2):
-        //      lane 1 is decided first, straight from the truth tables.
-        uint64_t XL = 0, XR = 0, flips = 0, todo = live ? valid : 0ull;
-        if (QA) {
+        // ---- monomials of the 4 neighbour-disagreement masks (shared by all boolean functions)
+        uint32_t mlo[16], mhi[16];
+        mlo[0] = mhi[0] = 0xFFFFFFFFu;
+#pragma unroll
+        for (int n = 0; n < 4; n++) {
+            const uint32_t lo = (uint32_t)x[n], hi = (uint32_t)(x[n] >> 32);
+#pragma unroll
+            for (int S = 0; S < (1 << n); S++) {
+                mlo[(1 << n) + S] = S ? (mlo[S] & lo) : lo;
+                mhi[(1 << n) + S] = S ? (mhi[S] & hi) : hi;
+            }
+        }
+        // "accept by sign" / "needs a uniform" of Trotter class c for all 64 lanes at once: a 4-input
+        // boolean function of the disagreement masks in algebraic normal form.  No pattern of a class
+        // needs a uniform for ~70% of (spin, class) pairs at T << J: block-uniform skip.
+        auto anf_acc = [&](int c) -> uint64_t {
+            uint32_t lo = tab.cacc[c][0], hi = lo;
+#pragma unroll
+            for (int S = 1; S < 16; S++) {
+                const uint32_t ca = tab.cacc[c][S];
+                lo ^= ca & mlo[S];
+                hi ^= ca & mhi[S];
+            }
+            return ((uint64_t)hi << 32) | lo;
+        };
+        auto anf_need = [&](int c) -> uint64_t {
+            if (tab.hneed[c] == 0u) return 0ull;
+            uint32_t lo = tab.cneed[c][0], hi = lo;
+#pragma unroll
+            for (int S = 1; S < 16; S++) {
+                const uint32_t cn = tab.cneed[c][S];
+                lo ^= cn & mlo[S];
+                hi ^= cn & mhi[S];
+            }
+            return ((uint64_t)hi << 32) | lo;
+        };
+
+        uint64_t result;
+        if (!QA) {
+            // ---- SA: no Trotter terms, one class
+            const uint64_t todo = live ? valid : 0ull;
+            uint64_t ACC = anf_acc(0) & todo;
+            const uint64_t NEED = anf_need(0) & todo;
+            if (__any_sync(0xffffffffu, NEED != 0))
+                ACC |= resolve_draws<QA>(NEED, x, 0ull, 0ull, tab, queue, (uint32_t)i, sweep, prow_warp, a.k0, a.k1);
+            result = w ^ ACC;
+        } else if (TROT == 0) {
+            // ---- reference Trotter neighbours: slices P-1 (old value for everyone; itself for lane
+            //      P-1) and 1 (old for lane 0, itself for lane 1, new for lanes >= 2): lane 1 is decided
+            //      first, straight from the truth tables.
+            uint64_t flips = 0;
             const uint64_t bl = ((w >> (lanes - 1)) & 1ull) ? ~0ull : 0ull;
             const uint64_t br_old = ((w >> 1) & 1ull) ? ~0ull : 0ull;
-            XL = (w ^ bl) & ~(1ull << (lanes - 1));
+            const uint64_t XL = (w ^ bl) & ~(1ull << (lanes - 1));
             const uint32_t c1 = (uint32_t)(XL >> 1) & 1u;               // right neighbour of lane 1 is itself
             const uint32_t p1 = pattern_at(x, 1);
             if (live) {
@@ -354,57 +400,50 @@ __global__ void __launch_bounds__(FAST_THREADS, 5) colour_sweep_fast(const FastA
                         flips = 2ull;
             }
             const uint64_t br_new = br_old ^ (flips ? ~0ull : 0ull);
-            XR = ((w ^ br_new) & ~1ull) | ((w ^ br_old) & 1ull);       // lane 0 sees the old bit 1
-            todo &= ~2ull;
-        }
-
-        // ---- "accept by sign" and "needs a uniform" for all 64 lanes at once: per Trotter class a
-        //      4-input boolean function of the disagreement masks, evaluated in algebraic normal form
-        uint64_t ACC = 0, NEED = 0;
-        {
-            uint32_t mlo[16], mhi[16];
-            mlo[0] = mhi[0] = 0xFFFFFFFFu;
-#pragma unroll
-            for (int n = 0; n < 4; n++) {
-                const uint32_t lo = (uint32_t)x[n], hi = (uint32_t)(x[n] >> 32);
-#pragma unroll
-                for (int S = 0; S < (1 << n); S++) {
-                    mlo[(1 << n) + S] = S ? (mlo[S] & lo) : lo;
-                    mhi[(1 << n) + S] = S ? (mhi[S] & hi) : hi;
-                }
-            }
+            const uint64_t XR = ((w ^ br_new) & ~1ull) | ((w ^ br_old) & 1ull);   // lane 0 sees the old bit 1
+            const uint64_t todo = live ? (valid & ~2ull) : 0ull;
+            uint64_t ACC = 0, NEED = 0;
 #pragma unroll
             for (int c = 0; c < NC; c++) {
-                // lanes of Trotter class c
-                const uint64_t Cc = !QA ? ~0ull : (c == 0 ? ~(XL | XR) : (c == 1 ? (XL ^ XR) : (XL & XR)));
-                const uint32_t clo = (uint32_t)Cc, chi = (uint32_t)(Cc >> 32);
-                uint32_t alo = tab.cacc[c][0], ahi = alo;
-#pragma unroll
-                for (int S = 1; S < 16; S++) {
-                    const uint32_t ca = tab.cacc[c][S];
-                    alo ^= ca & mlo[S];
-                    ahi ^= ca & mhi[S];
-                }
-                ACC |= ((uint64_t)(ahi & chi) << 32) | (alo & clo);
-                // no pattern of this class needs a uniform for ~70% of (spin, class) pairs at T << J:
-                // block-uniform skip
-                if (tab.hneed[c] != 0u) {
-                    uint32_t nlo = tab.cneed[c][0], nhi = nlo;
-#pragma unroll
-                    for (int S = 1; S < 16; S++) {
-                        const uint32_t cn = tab.cneed[c][S];
-                        nlo ^= cn & mlo[S];
-                        nhi ^= cn & mhi[S];
-                    }
-                    NEED |= ((uint64_t)(nhi & chi) << 32) | (nlo & clo);
-                }
+                const uint64_t Cc = (c == 0 ? ~(XL | XR) : (c == 1 ? (XL ^ XR) : (XL & XR))) & todo;
+                ACC |= anf_acc(c) & Cc;
+                NEED |= anf_need(c) & Cc;
             }
+            if (__any_sync(0xffffffffu, NEED != 0))
+                ACC |= resolve_draws<QA>(NEED, x, XL, XR, tab, queue, (uint32_t)i, sweep, prow_warp, a.k0, a.k1);
+            result = w ^ flips ^ ACC;
+        } else {
+            // ---- periodic Trotter neighbours k-1, k+1: even slices first, then odd slices (the lanes
+            //      of one pass do not see each other).  With an odd slice count lanes 0 and P-1 are
+            //      both even and adjacent: lane P-1 gets a pass of its own after the even pass.
+            uint64_t Fa[NC], Fn[NC];
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                Fa[c] = anf_acc(c);
+                Fn[c] = anf_need(c);
+            }
+            const uint64_t evens = 0x5555555555555555ull & valid, odds = 0xAAAAAAAAAAAAAAAAull & valid;
+            const uint64_t top = 1ull << (lanes - 1);
+            const bool oddP = (lanes & 1) != 0;
+            uint64_t cur = w;
+#pragma unroll 1
+            for (int pass = 0; pass < 3; pass++) {
+                uint64_t sel = pass == 0 ? (oddP ? (evens & ~top) : evens) : (pass == 1 ? (oddP ? top : 0ull) : odds);
+                if (!live) sel = 0ull;
+                const uint64_t Lw = ((cur << 1) | (cur >> (lanes - 1))) & valid;     // bit k = slice k-1
+                const uint64_t Rw = ((cur >> 1) | (cur << (lanes - 1))) & valid;     // bit k = slice k+1
+                const uint64_t XL = cur ^ Lw, XR = cur ^ Rw;
+                const uint64_t C0 = ~(XL | XR), C1 = XL ^ XR, C2 = XL & XR;
+                uint64_t ACC = ((C0 & Fa[0]) | (C1 & Fa[1]) | (C2 & Fa[NC - 1])) & sel;
+                const uint64_t NEED = ((C0 & Fn[0]) | (C1 & Fn[1]) | (C2 & Fn[NC - 1])) & sel;
+                // lanes of this pass have not flipped yet, so their rows of x are still current
+                if (__any_sync(0xffffffffu, NEED != 0))
+                    ACC |= resolve_draws<QA>(NEED, x, XL, XR, tab, queue, (uint32_t)i, sweep, prow_warp, a.k0, a.k1);
+                cur ^= ACC;
+            }
+            result = cur;
         }
-        ACC &= todo;
-        NEED &= todo;
-        if (__any_sync(0xffffffffu, NEED != 0))
-            ACC |= resolve_draws<QA>(NEED, x, XL, XR, tab, queue, (uint32_t)i, sweep, prow_warp, a.k0, a.k1);
-        if (live) wrow[(size_t)i * nrows] = w ^ flips ^ ACC;
+        if (live) wrow[(size_t)i * nrows] = result;
     }
 
     // ---- publish: all stores of the block happen-before the flag
@@ -420,7 +459,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 5) colour_sweep_fast(const FastA
 // Runs `nsweeps` sweeps in as few launches as the grid-size limit allows (normally one).
 // members/level: device arrays, level-major spin order and level per spin; either one list for
 // all sweeps or one per sweep.  d_jp2/d_invT: per sweep.
-int launch_fast_sweeps(piqmc_ctx *c, int qa, int nsweeps, const int32_t *d_members, const int32_t *d_level,
+int launch_fast_sweeps(piqmc_ctx *c, int qa, int trotter, int nsweeps, const int32_t *d_members, const int32_t *d_level,
                        const int32_t *d_sweepoff, int nperiods_extra, int per_sweep_lists, const float *d_jp2,
                        const float *d_invT, uint64_t seed, uint32_t row0, uint32_t sweep0)
 {
@@ -486,8 +525,9 @@ int launch_fast_sweeps(piqmc_ctx *c, int qa, int nsweeps, const int32_t *d_membe
         const size_t nunits = (size_t)(ns + nperiods_extra) * per_sweep;
         ticket_base += (unsigned int)nunits;
         dim3 block(FAST_THREADS), grid((unsigned)nunits);
-        if (qa) colour_sweep_fast<true><<<grid, block, 0, c->stream>>>(a);
-        else    colour_sweep_fast<false><<<grid, block, 0, c->stream>>>(a);
+        if (!qa)          colour_sweep_fast<false, 0><<<grid, block, 0, c->stream>>>(a);
+        else if (trotter) colour_sweep_fast<true, 1><<<grid, block, 0, c->stream>>>(a);
+        else              colour_sweep_fast<true, 0><<<grid, block, 0, c->stream>>>(a);
         c->launches++;
         PIQMC_CUDA(cudaGetLastError());
     }

@@ -141,13 +141,15 @@ int launch_energy(piqmc_ctx *c);
 int launch_energy_coo(piqmc_ctx *c, int nspins, int nnz, const int32_t *d_row, const int32_t *d_col,
                       const double *d_val, int nconfs, const int8_t *d_spins, double *d_out);
 // the production kernel: nsweeps sweeps in one dataflow launch (colour_fast.cu)
-int launch_fast_sweeps(piqmc_ctx *c, int qa, int nsweeps, const int32_t *d_members, const int32_t *d_level,
+int launch_fast_sweeps(piqmc_ctx *c, int qa, int trotter, int nsweeps, const int32_t *d_members, const int32_t *d_level,
                        const int32_t *d_sweepoff, int nperiods_extra, int per_sweep_lists, const float *d_jp2,
                        const float *d_invT, uint64_t seed, uint32_t row0, uint32_t sweep0);
 // variant: 0 auto (fast kernel when the graph qualifies and there are enough rows to fill its
 // 128-thread blocks), 1 generic, 2 fast whenever the graph qualifies (used by the parity tests)
 static inline bool piqmc_fast_ok(const piqmc_ctx *c, int qa, int trotter)
 {
-    if (c->variant == 1 || c->maxnb > 4 || (qa && trotter != 0)) return false;
+    (void)qa;
+    (void)trotter;
+    if (c->variant == 1 || c->maxnb > 4) return false;
     return c->variant == 2 || c->nrows >= 32;
 }
