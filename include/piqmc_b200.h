@@ -159,6 +159,11 @@ int piqmc_qa_colour(piqmc_handle h, const double *sched, int nsched, int mcsteps
 /* Classical SA sweeps over the resident state (lanes = 64 replicas per word, sa.Anneal rules). */
 int piqmc_sa_colour(piqmc_handle h, const double *sched, int nsched, int mcsteps,
                     uint64_t seed, uint32_t row0, uint32_t sweep0, const int32_t *orders);
+/* World-line (global) moves for piqmc_qa_colour: after the local moves of a spin, attempt to flip
+ * it in ALL slices at once (the Trotter terms cancel; ediff = slice-summed in-slice term, same
+ * Metropolis rule).  A capability the reference does not have (BASELINE.json north_star); off by
+ * default; needs maxnb <= 4.  Specification: oracle/piqmc_oracle.c, oracle_qa_colour. */
+int piqmc_set_global_moves(piqmc_handle h, int enable);
 /* kernel variant selection for piqmc_qa_colour / piqmc_sa_colour: 0 = auto, 1 = generic,
  * 2 = table-lookup fast path (falls back to generic when the graph does not qualify) */
 int piqmc_set_variant(piqmc_handle h, int variant);

@@ -235,7 +235,7 @@ def _orders(orders, nsweeps, n):
 
 
 def qa_colour(sched, mcsteps, slices, temp, idx, J, color, spins, seed, replica0=0, sweep0=0, trotter=0,
-              orders=None):
+              orders=None, global_moves=False):
     """spins int8[R,N,P] in place.  orders int32[nsweeps,N]: sequential sweeps in those visiting
     orders instead of colour classes."""
     sched = np.ascontiguousarray(sched, dtype=np.float64)
@@ -245,6 +245,7 @@ def qa_colour(sched, mcsteps, slices, temp, idx, J, color, spins, seed, replica0
     assert spins.dtype == np.int8 and spins.flags.c_contiguous and spins.ndim == 3
     R, N, P = spins.shape
     assert P == slices and idx.shape == J.shape == (N, idx.shape[1])
+    ctypes.c_int.in_dll(lib(), "oracle_colour_global_moves").value = 1 if global_moves else 0
     lib().oracle_qa_colour(_p(sched, c_dp), sched.size, mcsteps, slices, ctypes.c_float(temp),
                            N, idx.shape[1], _p(idx, c_ip), _p(J, c_fp), int(color.max()) + 1,
                            _p(color, c_ip), R, _p(spins, c_bp), seed, replica0, sweep0, trotter,

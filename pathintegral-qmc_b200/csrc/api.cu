@@ -714,6 +714,13 @@ int piqmc_state_download_words(piqmc_handle h, uint64_t *words)
 void *piqmc_state_devptr(piqmc_handle h) { return h ? (void *)h->d_words : nullptr; }
 void *piqmc_energy_devptr(piqmc_handle h) { return h ? (void *)h->d_energy : nullptr; }
 
+int piqmc_set_global_moves(piqmc_handle h, int enable)
+{
+    PIQMC_REQUIRE(h != nullptr, PIQMC_EINVAL, "null handle");
+    h->global_moves = enable ? 1 : 0;
+    return PIQMC_OK;
+}
+
 int piqmc_set_variant(piqmc_handle h, int variant)
 {
     PIQMC_REQUIRE(h != nullptr && variant >= 0 && variant <= 2, PIQMC_EINVAL, "variant must be 0, 1 or 2");
@@ -731,6 +738,8 @@ int piqmc_qa_colour(piqmc_handle h, const double *sched, int nsched, int mcsteps
     PIQMC_REQUIRE(trotter == 0 || trotter == 1, PIQMC_EINVAL, "trotter must be 0 or 1");
     PIQMC_REQUIRE(h->lanes >= 2, PIQMC_EINVAL, "slices must be >= 2");
     PIQMC_REQUIRE((float)h->lanes * temp != 0.0f && temp != 0.0f, PIQMC_EZERODIV, "float division");
+    PIQMC_REQUIRE(!h->global_moves || piqmc_fast_ok(h, 1, trotter), PIQMC_EINVAL,
+                  "world-line moves need the table kernel (maxnb <= 4, variant != 1, >= 32 rows)");
     std::vector<float> jp2(std::max(nsched, 1)), invT(std::max(nsched, 1), 1.0f / temp);
     for (int f = 0; f < nsched; f++) jp2[f] = 2.0f * piqmc_jperp(sched[f], h->lanes, temp);
     return run_colour_sweeps(h, 1, trotter, nsched, mcsteps, jp2, invT, seed, replica0, sweep0, orders);

@@ -53,6 +53,7 @@ struct SpinTable {
     uint32_t cneed[3][16];   // ... of "needs a uniform"
     uint32_t thr[3][16];     // acceptance threshold of pattern p in class c
     uint32_t hacc[3], hneed[3];   // truth tables (bit p)
+    float insum[16];         // in-slice energy difference of pattern p (no Trotter term): world-line moves
 };
 
 // Per-spin decision tables, built by warp c for Trotter class c without any block barrier
@@ -67,6 +68,7 @@ __device__ __forceinline__ void build_table_warp(SpinTable &tab, int c, int i, i
     float e = 0.0f;
     for (int n = 0; n < maxnb; n++)
         e = __fadd_rn(e, flip_sign(-2.0f * J_t[(size_t)n * nspins + i], (uint32_t)(p >> n) & 1u));
+    if (c == 0 && lane < 16) tab.insum[p] = e;
     if (QA) {
         const float tsum = (c == 0) ? -2.0f * jp2 : (c == 1 ? 0.0f : 2.0f * jp2);   // exact
         e = __fadd_rn(e, tsum);
@@ -234,6 +236,7 @@ struct FastArgs {
     unsigned int *ticket;
     int nspins, nrows, maxnb, lanes, nchunks, rows_per_block;
     int per_sweep_lists;        // members/level advance by N per sweep
+    int global_moves;           // QA: attempt a world-line move after the local moves of every spin
     uint32_t k0, k1, row0, sweep0, tag0;
     unsigned int ticket_base;   // units handed out by earlier launches of the same run
     unsigned int poll_ns;       // back-off between polls of a completion flag (0 = spin)
@@ -443,6 +446,35 @@ __global__ void __launch_bounds__(FAST_THREADS, 5) colour_sweep_fast(const FastA
             }
             result = cur;
         }
+        if (QA && a.global_moves) {
+            // ---- world-line move: flip the spin in all slices at once.  The Trotter terms cancel;
+            //      ediff = sum_p count[p] * insum[p] over the patterns of the UPDATED word (float64
+            //      accumulation in pattern order, as oracle_qa_colour states it).
+            const uint64_t d = w ^ result;                       // own flips toggle every disagreement bit
+            uint64_t xa[2][2], xb[2][2];                         // [literal value][variable]
+#pragma unroll
+            for (int n = 0; n < 2; n++) {
+                const uint64_t v0 = (n < maxnb) ? (x[n] ^ d) : 0ull, v1 = (n + 2 < maxnb) ? (x[n + 2] ^ d) : 0ull;
+                xa[1][n] = v0; xa[0][n] = ~v0;
+                xb[1][n] = v1; xb[0][n] = ~v1;
+            }
+            double accd = 0.0;
+#pragma unroll
+            for (int pat = 0; pat < 16; pat++) {
+                const uint64_t mt = xa[pat & 1][0] & xa[(pat >> 1) & 1][1] & xb[(pat >> 2) & 1][0] &
+                                    xb[(pat >> 3) & 1][1] & valid;
+                accd += (double)__popcll(mt) * (double)tab.insum[pat];
+            }
+            const float g = __fadd_rn((float)accd, 0.0f);
+            bool flip = g > 0.0f;
+            if (!flip) {
+                const float xg = __fmul_rn(g, a.invT[s]);
+                if (xg >= PIQMC_XCUT)
+                    flip = philox4x32_10((uint32_t)i, PIQMC_STREAM_GLOBAL << 16, sweep, a.row0 + (uint32_t)row,
+                                         a.k0, a.k1).x < colour_thresh(xg);
+            }
+            if (flip) result ^= valid;
+        }
         if (live) wrow[(size_t)i * nrows] = result;
     }
 
@@ -505,6 +537,7 @@ int launch_fast_sweeps(piqmc_ctx *c, int qa, int trotter, int nsweeps, const int
     a.k0 = (uint32_t)seed;
     a.k1 = (uint32_t)(seed >> 32);
     a.row0 = row0;
+    a.global_moves = c->global_moves;
     a.poll_ns = 0;
     if (const char *e = getenv("PIQMC_POLL_NS")) a.poll_ns = (unsigned int)atoi(e);
 

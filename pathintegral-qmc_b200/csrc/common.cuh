@@ -71,6 +71,7 @@ struct piqmc_ctx {
     size_t epart_elems = 0;
 
     int variant = 0;
+    int global_moves = 0;           // QA world-line moves (fast kernel only)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -78,6 +79,7 @@ struct piqmc_ctx {
 // ------------------------------------------------------------------------------------------
 #define PIQMC_STREAM_SWEEP 0u
 #define PIQMC_STREAM_INIT 1u
+#define PIQMC_STREAM_GLOBAL 2u
 #define PIQMC_XCUT (-22.0f)
 
 struct u32x4 {

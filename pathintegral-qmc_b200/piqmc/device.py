@@ -88,6 +88,10 @@ class Device:
     def set_variant(self, variant):
         check(lib.piqmc_set_variant(self._h, int(variant)))
 
+    def set_global_moves(self, enable):
+        """World-line (all-slices) moves after the local moves of every spin (QA, maxnb <= 4)."""
+        check(lib.piqmc_set_global_moves(self._h, 1 if enable else 0))
+
     # ------------------------------------------------------------------ graph
     def set_graph(self, nbs, color=None):
         """Upload the neighbour table (and, for the colour paths, a proper colouring).

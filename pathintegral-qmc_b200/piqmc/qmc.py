@@ -102,7 +102,7 @@ def QuantumAnneal_parallel(sched, mcsteps, slices, temp, nspins, confs, nbs, nth
 
 def QuantumAnnealReplicas(sched, mcsteps, slices, temp, nspins, spins0, nbs, seed, order="natural",
                           color=None, replica0=0, trotter="reference", device=None, energies=True,
-                          tile=True, nreplicas=None, download=True, words_out=None):
+                          tile=True, nreplicas=None, download=True, words_out=None, global_moves=False):
     """Production PIQMC: R replicas x `slices` Trotter slices x nspins, one uint64 word per
     (replica, spin) holding all slices, colour-class Metropolis sweeps with Philox4x32-10 keyed by
     (seed; spin, slice, sweep, replica0 + r), J_perp recomputed per schedule step.
@@ -116,6 +116,8 @@ def QuantumAnnealReplicas(sched, mcsteps, slices, temp, nspins, spins0, nbs, see
                        from the natural-order sweep, see DESIGN.md);
         int32[N] / int32[nsweeps,N]  explicit visiting order(s).
     color: explicit colour classes (overrides order).
+    global_moves: also attempt a world-line move (flip the spin in all slices at once) after the
+        local moves of every spin -- not in the reference; off by default.
 
     spins0: int8[R, nspins] copied to every slice (tile=True, the reference's
             np.tile(spinVector, (P,1)).T start), or int8[R, slices, nspins] (tile=False), or None
@@ -146,8 +148,12 @@ def QuantumAnnealReplicas(sched, mcsteps, slices, temp, nspins, spins0, nbs, see
     else:
         d.state_upload_spins(spins0, tile=tile)
     t.append(time.perf_counter())
-    d.qa_colour(sched, int(mcsteps), temp, seed, replica0=replica0, trotter=TROTTER[trotter],
-                orders=orders)
+    d.set_global_moves(global_moves)
+    try:
+        d.qa_colour(sched, int(mcsteps), temp, seed, replica0=replica0, trotter=TROTTER[trotter],
+                    orders=orders)
+    finally:
+        d.set_global_moves(False)
     t.append(time.perf_counter())
     out = {"energies": None, "words": None}
     if energies:

@@ -373,3 +373,34 @@ def test_fast_kernel_sa_many_rows_bit_exact(golden, dev):
         O.sa_colour(sched, 2, idx, J32, color, want, seed=77, row0=9)
         out = sa.AnnealReplicas(sched, 2, init, nbs, 77, color=color, row0=9, device=dev)
         assert np.array_equal(out["spins"], want)
+
+
+# ------------------------------------------------------------------- world-line (global) moves
+@pytest.mark.parametrize("trotter", [0, 1])
+@pytest.mark.parametrize("inst,P,T", [("boixo", 6, 0.3), ("inst_0_32x32", 20, 0.2), ("inst_0_32x32", 64, 0.01)])
+def test_world_line_moves_bit_exact(golden, dev, inst, P, T, trotter):
+    """World-line moves (a north_star capability the reference does not have): the kernel against
+    this repository's CPU statement of them, bit for bit, and a sanity check that they do act."""
+    import piqmc.tools as tools
+    nbs, idx, J32, color = _graph(golden, inst)
+    n, R, seed = NSPINS[inst], 40, 4711
+    sched = np.linspace(1.5, 0.2, 5)
+    init = O.colour_init_spins(seed, 0, R, n)
+    want = np.repeat(init[:, :, None], P, axis=2).copy()
+    O.qa_colour(sched, 1, P, T, idx, J32, color, want, seed, trotter=trotter, global_moves=True)
+    plain = np.repeat(init[:, :, None], P, axis=2).copy()
+    O.qa_colour(sched, 1, P, T, idx, J32, color, plain, seed, trotter=trotter, global_moves=False)
+    dev.set_graph(nbs, color)
+    dev.set_variant(2)
+    dev.set_global_moves(True)
+    try:
+        dev.state_alloc(R, P)
+        dev.state_init_random(seed, 0, tile=True)
+        dev.qa_colour(sched, 1, T, seed, trotter=trotter)
+        got = np.transpose(tools.UnpackWords(dev.state_download_words(), P), (0, 2, 1))
+    finally:
+        dev.set_global_moves(False)
+        dev.set_variant(0)
+    assert np.array_equal(want, got)
+    if T > 0.1:
+        assert not np.array_equal(want, plain)          # at these temperatures some global moves are accepted
