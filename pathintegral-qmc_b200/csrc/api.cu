@@ -46,8 +46,7 @@ void free_graph(piqmc_ctx *c)
     free_dev(c->d_J32_t);
     free_dev(c->d_members);
     free_dev(c->d_level);
-    free_dev(c->d_pmembers);
-    free_dev(c->d_psweepoff);
+    free_dev(c->d_recs);
     free_dev(c->d_done);
     c->flow_nchunks = 0;
     c->color_off.clear();
@@ -112,6 +111,31 @@ static void bucket_members(int nspins, int ncolors, const int32_t *color, std::v
     for (int i = 0; i < nspins; i++) members[fill[color[i]]++] = i;
 }
 
+// unit records (dataflow kernel) for the members listed in `order`, given the level of every spin
+static void build_unit_recs(const piqmc_ctx *h, const int32_t *level, const int32_t *order,
+                            const int32_t *sweepoff, PiqmcUnitRec *out)
+{
+    const int mb = h->maxnb < 4 ? h->maxnb : 4;
+    for (int k = 0; k < h->nspins; k++) {
+        const int i = order[k];
+        PiqmcUnitRec &r = out[k];
+        r.spin = i;
+        r.sweepoff = sweepoff ? sweepoff[k] : 0;
+        r.pad = 0;
+        for (int n = 0; n < 4; n++) {
+            r.nb[n] = i;
+            r.J[n] = 0.0f;
+            r.dep[n] = 0;
+            if (n < mb) {
+                const size_t e = (size_t)i * h->maxnb + n;
+                r.nb[n] = h->h_idx[e];
+                r.J[n] = h->h_J32[e];
+                if (h->h_live[e]) r.dep[n] = level[h->h_idx[e]] < level[i] ? 2 : 1;
+            }
+        }
+    }
+}
+
 static int apply_colouring(piqmc_ctx *h, int ncolors, const int32_t *color, bool validate)
 {
     if (validate) {
@@ -150,8 +174,11 @@ static int apply_colouring(piqmc_ctx *h, int ncolors, const int32_t *color, bool
         pm[k] = order[k];
         po[k] = color[order[k]] / D;
     }
-    PIQMC_CUDA(cudaMemcpy(h->d_pmembers, pm.data(), (size_t)h->nspins * sizeof(int32_t), cudaMemcpyHostToDevice));
-    PIQMC_CUDA(cudaMemcpy(h->d_psweepoff, po.data(), (size_t)h->nspins * sizeof(int32_t), cudaMemcpyHostToDevice));
+    if (h->maxnb <= 4) {
+        std::vector<PiqmcUnitRec> recs(h->nspins);
+        build_unit_recs(h, color, pm.data(), po.data(), recs.data());
+        PIQMC_CUDA(cudaMemcpy(h->d_recs, recs.data(), recs.size() * sizeof(PiqmcUnitRec), cudaMemcpyHostToDevice));
+    }
     h->flow_extra = (ncolors + D - 1) / D - 1;
     h->ncolors = ncolors;
     return PIQMC_OK;
@@ -223,8 +250,8 @@ static int run_colour_sweeps(piqmc_ctx *h, int qa, int trotter, int nsched, int 
 
     if (!orders) {
         if (fast) {
-            TRY(launch_fast_sweeps(h, qa, trotter, (int)nsweeps, h->d_pmembers, h->d_level, h->d_psweepoff, h->flow_extra, 0,
-                                   d_jp2.p, d_invT.p, seed, row0, sweep0));
+            TRY(launch_fast_sweeps(h, qa, trotter, (int)nsweeps, h->d_recs, h->flow_extra, 0, d_jp2.p, d_invT.p, seed,
+                                   row0, sweep0));
             // the per-sweep parameter arrays must outlive the launch
             PIQMC_CUDA(cudaStreamSynchronize(h->stream));
             return PIQMC_OK;
@@ -241,11 +268,14 @@ static int run_colour_sweeps(piqmc_ctx *h, int qa, int trotter, int nsched, int 
 
     // per-sweep visiting orders: level-colour each sweep on the host, ship member lists (and
     // levels) in chunks of sweeps (bounded device memory)
-    const size_t chunk = std::max<size_t>(1, std::min<size_t>(nsweeps, (size_t)(64u << 20) / ((size_t)N * 4)));
-    DevBuf<int32_t> d_mem, d_lev;
-    PIQMC_CUDA(d_mem.alloc(chunk * N));
-    if (fast) PIQMC_CUDA(d_lev.alloc(chunk * N));
+    const size_t chunk = std::max<size_t>(1, std::min<size_t>(nsweeps, (size_t)(64u << 20) /
+                                                                        ((size_t)N * (fast ? sizeof(PiqmcUnitRec) : 4))));
+    DevBuf<int32_t> d_mem;
+    DevBuf<PiqmcUnitRec> d_rec;
+    if (fast) PIQMC_CUDA(d_rec.alloc(chunk * N));
+    else      PIQMC_CUDA(d_mem.alloc(chunk * N));
     std::vector<int32_t> members(chunk * N), levels(chunk * N);
+    std::vector<PiqmcUnitRec> recs(fast ? chunk * N : 0);
     std::vector<std::vector<int>> offs(chunk);
     for (size_t base = 0; base < nsweeps; base += chunk) {
         const size_t m = std::min(chunk, nsweeps - base);
@@ -254,16 +284,17 @@ static int run_colour_sweeps(piqmc_ctx *h, int qa, int trotter, int nsched, int 
             const int nlev = order_levels(N, h->maxnb, h->h_idx.data(), h->h_live.data(),
                                           orders + (base + s) * N, lev);
             bucket_members(N, nlev, lev, offs[s], members.data() + s * N);
+            if (fast) build_unit_recs(h, lev, members.data() + s * N, nullptr, recs.data() + s * N);
         }
         PIQMC_CUDA(cudaStreamSynchronize(h->stream));     // previous chunk's lists no longer in use
-        PIQMC_CUDA(cudaMemcpyAsync(d_mem.p, members.data(), m * N * sizeof(int32_t), cudaMemcpyHostToDevice,
-                                   h->stream));
         if (fast) {
-            PIQMC_CUDA(cudaMemcpyAsync(d_lev.p, levels.data(), m * N * sizeof(int32_t), cudaMemcpyHostToDevice,
+            PIQMC_CUDA(cudaMemcpyAsync(d_rec.p, recs.data(), m * N * sizeof(PiqmcUnitRec), cudaMemcpyHostToDevice,
                                        h->stream));
-            TRY(launch_fast_sweeps(h, qa, trotter, (int)m, d_mem.p, d_lev.p, nullptr, 0, 1, d_jp2.p + base, d_invT.p + base,
-                                   seed, row0, sweep0 + (uint32_t)base));
+            TRY(launch_fast_sweeps(h, qa, trotter, (int)m, d_rec.p, 0, 1, d_jp2.p + base, d_invT.p + base, seed, row0,
+                                   sweep0 + (uint32_t)base));
         } else {
+            PIQMC_CUDA(cudaMemcpyAsync(d_mem.p, members.data(), m * N * sizeof(int32_t), cudaMemcpyHostToDevice,
+                                       h->stream));
             for (size_t s = 0; s < m; s++) {
                 const int f = (int)((base + s) / mcsteps);
                 const std::vector<int> &off = offs[s];
@@ -462,6 +493,7 @@ int piqmc_set_graph(piqmc_handle h, int nspins, int maxnb, const int32_t *idx, c
     h->nspins = nspins;
     h->maxnb = maxnb;
     h->h_idx.assign(idx, idx + ne);
+    h->h_J32 = j32;
     h->h_live.resize(ne);
     for (int i = 0; i < nspins; i++)
         for (int n = 0; n < maxnb; n++) {
@@ -470,8 +502,7 @@ int piqmc_set_graph(piqmc_handle h, int nspins, int maxnb, const int32_t *idx, c
         }
     PIQMC_CUDA(cudaMalloc(&h->d_members, (size_t)nspins * sizeof(int32_t)));
     PIQMC_CUDA(cudaMalloc(&h->d_level, (size_t)nspins * sizeof(int32_t)));
-    PIQMC_CUDA(cudaMalloc(&h->d_pmembers, (size_t)nspins * sizeof(int32_t)));
-    PIQMC_CUDA(cudaMalloc(&h->d_psweepoff, (size_t)nspins * sizeof(int32_t)));
+    PIQMC_CUDA(cudaMalloc(&h->d_recs, (size_t)nspins * sizeof(PiqmcUnitRec)));
     if (color) TRY(apply_colouring(h, ncolors, color, false));
     // a new graph invalidates any resident state
     free_state(h);

@@ -60,14 +60,15 @@ struct SpinTable {
 // (the caller synchronises once).  Trotter class of a lane = number of Trotter neighbours it
 // disagrees with (0,1,2): tsum = -2*jp2, +0, +2*jp2.
 template <bool QA>
-__device__ __forceinline__ void build_table_warp(SpinTable &tab, int c, int i, int nspins, int maxnb,
-                                                 const float *__restrict__ J_t, float jp2, float invT)
+__device__ __forceinline__ void build_table_warp(SpinTable &tab, int c, const float (&Jn)[4], float jp2,
+                                                 float invT)
 {
     const int lane = threadIdx.x & 31;
     const int p = lane & 15;                     // lanes 16..31 mirror lanes 0..15
     float e = 0.0f;
-    for (int n = 0; n < maxnb; n++)
-        e = __fadd_rn(e, flip_sign(-2.0f * J_t[(size_t)n * nspins + i], (uint32_t)(p >> n) & 1u));
+#pragma unroll
+    for (int n = 0; n < 4; n++)                  // unused columns carry J = 0: adding +-0 changes nothing
+        e = __fadd_rn(e, flip_sign(-2.0f * Jn[n], (uint32_t)(p >> n) & 1u));
     if (c == 0 && lane < 16) tab.insum[p] = e;
     if (QA) {
         const float tsum = (c == 0) ? -2.0f * jp2 : (c == 1 ? 0.0f : 2.0f * jp2);   // exact
@@ -225,11 +226,7 @@ __device__ __forceinline__ void st_release(uint32_t *p, uint32_t v)
 
 struct FastArgs {
     uint64_t *words;            // [N][nrows]
-    const int32_t *idx_t;       // [maxnb][N]
-    const float *J_t;           // [maxnb][N]
-    const int32_t *members;     // per sweep (or shared): spins in level-major order
-    const int32_t *level;       // per sweep (or shared): level of every spin
-    const int32_t *sweepoff;    // static colouring only: sweep lag of member m (NULL: none)
+    const PiqmcUnitRec *recs;   // per sweep (or shared): one record per member, in ticket order
     int nsweeps;                // sweeps covered by this launch
     const float *jp2, *invT;    // per sweep
     uint32_t *done;             // [N][nchunks] tag of the last finished sweep
@@ -263,33 +260,36 @@ __global__ void __launch_bounds__(FAST_THREADS, 5) colour_sweep_fast(const FastA
     const unsigned int rem = t - (unsigned int)q * per_sweep;
     const int chunk = (int)(rem % (unsigned int)a.nchunks);
     const unsigned int m = rem / (unsigned int)a.nchunks;
-    const int s = a.sweepoff ? q - a.sweepoff[m] : q;
+    // everything the unit needs about its spin in ONE 48-byte record (one L2 round trip instead
+    // of the member -> neighbour table -> level chain of dependent loads)
+    const int4 *rp = reinterpret_cast<const int4 *>(a.recs + (a.per_sweep_lists ? (size_t)q * a.nspins : 0) + m);
+    const int4 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2);
+    const int i = r0.x;
+    const int s = q - r0.y;
     if (s < 0 || s >= a.nsweeps) return;                           // ramp-up / ramp-down periods
-    const size_t lbase = a.per_sweep_lists ? (size_t)s * a.nspins : 0;
-    const int i = a.members[lbase + m];
+    const int nb[4] = {r0.z, r0.w, r1.x, r1.y};
+    const float Jn[4] = {__int_as_float(r1.z), __int_as_float(r1.w), __int_as_float(r2.x), __int_as_float(r2.y)};
+    const uint32_t deps = (uint32_t)r2.z;                           // byte n: 0 none, 1 wait s-1, 2 wait s
     const uint32_t tag = a.tag0 + (uint32_t)s + 1u;
     const uint32_t sweep = a.sweep0 + (uint32_t)s;
-    const int nspins = a.nspins, nrows = a.nrows, maxnb = a.maxnb, lanes = a.lanes;
-
-    int nb[4];
-#pragma unroll
-    for (int n = 0; n < 4; n++) nb[n] = (n < maxnb) ? a.idx_t[(size_t)n * nspins + i] : i;
+    const int nrows = a.nrows, maxnb = a.maxnb, lanes = a.lanes;
 
     // ---- warps 0..NC-1 build the decision tables while warp 3 waits until this unit's inputs
     //      are final (see the header comment); one barrier joins them
     const int warp = threadIdx.x >> 5;
     if (warp < NC) {
-        build_table_warp<QA>(tab, warp, i, nspins, maxnb, a.J_t, a.jp2[s], a.invT[s]);
+        build_table_warp<QA>(tab, warp, Jn, a.jp2[s], a.invT[s]);
     } else if (warp == FAST_WARPS - 1) {
-        const int q = threadIdx.x & 31;
-        if (q <= 4) {
+        const int ql = threadIdx.x & 31;
+        if (ql <= 4) {
             int j = i;
-            uint32_t want = tag - 1u;
+            uint32_t want = tag - 1u;                  // lane 4: the spin itself, previous sweep
             bool must = true;
-            if (q < 4) {
-                j = nb[q];
-                must = q < maxnb && j != i && a.J_t[(size_t)q * nspins + i] != 0.0f;
-                if (must && a.level[lbase + j] < a.level[lbase + i]) want = tag;
+            if (ql < 4) {
+                const uint32_t d = (deps >> (8 * ql)) & 0xFFu;
+                j = nb[ql];
+                must = d != 0u;
+                if (d == 2u) want = tag;
             }
             if (must) {
                 const uint32_t *flag = a.done + (size_t)j * a.nchunks + chunk;
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 5) colour_sweep_fast(const FastA
             w_nx = __ldcg(words + (size_t)i * nrows + row);
 #pragma unroll
             for (int n = 0; n < 4; n++)
-                if (n < maxnb && nb[n] != i) wn_nx[n] = __ldcg(words + (size_t)nb[n] * nrows + row);
+                if (nb[n] != i) wn_nx[n] = __ldcg(words + (size_t)nb[n] * nrows + row);
         }
     }
     for (int base = rbeg; base < rend; base += FAST_THREADS) {     // block-uniform trip count
@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 5) colour_sweep_fast(const FastA
                 w_nx = __ldcg(words + (size_t)i * nrows + rown);
 #pragma unroll
                 for (int n = 0; n < 4; n++)
-                    if (n < maxnb && nb[n] != i) wn_nx[n] = __ldcg(words + (size_t)nb[n] * nrows + rown);
+                    if (nb[n] != i) wn_nx[n] = __ldcg(words + (size_t)nb[n] * nrows + rown);
             }
         }
         const uint32_t prow_warp = a.row0 + (uint32_t)(base + (threadIdx.x & ~31));
@@ -480,10 +480,8 @@ __global__ void __launch_bounds__(FAST_THREADS, 5) colour_sweep_fast(const FastA
 
     // ---- publish: all stores of the block happen-before the flag
     __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        st_release(a.done + (size_t)i * a.nchunks + chunk, tag);
-    }
+    if (threadIdx.x == 0)                                           // release orders the block's stores
+        st_release(a.done + (size_t)i * a.nchunks + chunk, tag);   // (cumulative through the barrier)
 }
 
 }  // namespace
@@ -491,9 +489,9 @@ __global__ void __launch_bounds__(FAST_THREADS, 5) colour_sweep_fast(const FastA
 // Runs `nsweeps` sweeps in as few launches as the grid-size limit allows (normally one).
 // members/level: device arrays, level-major spin order and level per spin; either one list for
 // all sweeps or one per sweep.  d_jp2/d_invT: per sweep.
-int launch_fast_sweeps(piqmc_ctx *c, int qa, int trotter, int nsweeps, const int32_t *d_members, const int32_t *d_level,
-                       const int32_t *d_sweepoff, int nperiods_extra, int per_sweep_lists, const float *d_jp2,
-                       const float *d_invT, uint64_t seed, uint32_t row0, uint32_t sweep0)
+int launch_fast_sweeps(piqmc_ctx *c, int qa, int trotter, int nsweeps, const PiqmcUnitRec *d_recs,
+                       int nperiods_extra, int per_sweep_lists, const float *d_jp2, const float *d_invT,
+                       uint64_t seed, uint32_t row0, uint32_t sweep0)
 {
     if (nsweeps <= 0) return PIQMC_OK;
     // rows per block: the per-spin table is built once per block, so more rows per block is less
@@ -523,8 +521,6 @@ int launch_fast_sweeps(piqmc_ctx *c, int qa, int trotter, int nsweeps, const int
 
     FastArgs a;
     a.words = c->d_words;
-    a.idx_t = c->d_idx_t;
-    a.J_t = c->d_J32_t;
     a.done = c->d_done;
     a.ticket = c->d_ticket;
     a.nspins = c->nspins;
@@ -546,9 +542,7 @@ int launch_fast_sweeps(piqmc_ctx *c, int qa, int trotter, int nsweeps, const int
     unsigned int ticket_base = 0;
     for (int s0 = 0; s0 < nsweeps; s0 += max_sweeps) {
         const int ns = std::min(max_sweeps, nsweeps - s0);
-        a.members = d_members + (per_sweep_lists ? (size_t)s0 * c->nspins : 0);
-        a.level = d_level + (per_sweep_lists ? (size_t)s0 * c->nspins : 0);
-        a.sweepoff = d_sweepoff;
+        a.recs = d_recs + (per_sweep_lists ? (size_t)s0 * c->nspins : 0);
         a.nsweeps = ns;
         a.jp2 = d_jp2 + s0;
         a.invT = d_invT + s0;

@@ -31,6 +31,18 @@ void piqmc_set_error(const char *fmt, ...);
         }                                                                                  \
     } while (0)
 
+// One work-unit record of the dataflow kernel: everything a unit needs to know about its spin.
+struct alignas(16) PiqmcUnitRec {
+    int32_t spin;
+    int32_t sweepoff;     // sweep lag of this member in the period-major order (0 for per-sweep lists)
+    int32_t nb[4];        // neighbour spins (== spin for self entries and unused columns)
+    float J[4];           // couplings (0 for unused columns)
+    uint8_t dep[4];       // 0: nothing to wait for; 1: neighbour of a higher level (its previous sweep);
+                          // 2: neighbour of a lower level (its current sweep)
+    int32_t pad;
+};
+static_assert(sizeof(PiqmcUnitRec) == 48, "PiqmcUnitRec must be 48 bytes");
+
 // ------------------------------------------------------------------------------------------
 // device context
 // ------------------------------------------------------------------------------------------
@@ -51,9 +63,9 @@ struct piqmc_ctx {
     std::vector<int> color_off;     // ncolors+1 offsets into d_members
     std::vector<int32_t> h_idx;     // host copies for level colourings of per-sweep orders
     std::vector<uint8_t> h_live;    // J != 0 && idx != self
+    std::vector<float> h_J32;       // [N][maxnb]
     int32_t *d_level = nullptr;     // colour (level) of every spin (static colouring)
-    int32_t *d_pmembers = nullptr;  // spins sorted by (level mod D, level): period-major order
-    int32_t *d_psweepoff = nullptr; // level div D of those members
+    PiqmcUnitRec *d_recs = nullptr; // unit records, spins sorted by (level mod D, level): period-major order
     int flow_extra = 0;             // ceil(ncolors / D) - 1 ramp periods
     // dataflow sweep kernel (colour_fast.cu)
     uint32_t *d_done = nullptr;     // [N][flow_nchunks] tag of the last finished sweep
@@ -143,9 +155,9 @@ int launch_energy(piqmc_ctx *c);
 int launch_energy_coo(piqmc_ctx *c, int nspins, int nnz, const int32_t *d_row, const int32_t *d_col,
                       const double *d_val, int nconfs, const int8_t *d_spins, double *d_out);
 // the production kernel: nsweeps sweeps in one dataflow launch (colour_fast.cu)
-int launch_fast_sweeps(piqmc_ctx *c, int qa, int trotter, int nsweeps, const int32_t *d_members, const int32_t *d_level,
-                       const int32_t *d_sweepoff, int nperiods_extra, int per_sweep_lists, const float *d_jp2,
-                       const float *d_invT, uint64_t seed, uint32_t row0, uint32_t sweep0);
+int launch_fast_sweeps(piqmc_ctx *c, int qa, int trotter, int nsweeps, const PiqmcUnitRec *d_recs,
+                       int nperiods_extra, int per_sweep_lists, const float *d_jp2, const float *d_invT,
+                       uint64_t seed, uint32_t row0, uint32_t sweep0);
 // variant: 0 auto (fast kernel when the graph qualifies and there are enough rows to fill its
 // 128-thread blocks), 1 generic, 2 fast whenever the graph qualifies (used by the parity tests)
 static inline bool piqmc_fast_ok(const piqmc_ctx *c, int qa, int trotter)
