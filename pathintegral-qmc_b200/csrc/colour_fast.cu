@@ -239,8 +239,11 @@ struct FastArgs {
     unsigned int poll_ns;       // back-off between polls of a completion flag (0 = spin)
 };
 
-template <bool QA, int TROT>
-__global__ void __launch_bounds__(FAST_THREADS, 5) colour_sweep_fast(const FastArgs a)
+// MINB = resident blocks per SM the register allocation is capped for (7 -> 72 registers, 8 -> 64):
+// more resident blocks hide the per-unit latencies (ticket, record, flags) better, which matters
+// most when a unit has little work (few rows).
+template <bool QA, int TROT, int MINB>
+__global__ void __launch_bounds__(FAST_THREADS, MINB) colour_sweep_fast(const FastArgs a)
 {
     __shared__ SpinTable tab;
     __shared__ uint2 queues[FAST_WARPS][QCAP];
@@ -552,9 +555,17 @@ int launch_fast_sweeps(piqmc_ctx *c, int qa, int trotter, int nsweeps, const Piq
         const size_t nunits = (size_t)(ns + nperiods_extra) * per_sweep;
         ticket_base += (unsigned int)nunits;
         dim3 block(FAST_THREADS), grid((unsigned)nunits);
-        if (!qa)          colour_sweep_fast<false, 0><<<grid, block, 0, c->stream>>>(a);
-        else if (trotter) colour_sweep_fast<true, 1><<<grid, block, 0, c->stream>>>(a);
-        else              colour_sweep_fast<true, 0><<<grid, block, 0, c->stream>>>(a);
+        const bool wide = c->nrows >= 2048;       // measured on B200: 7 blocks/SM best at 4096 rows, 8 at 512
+        if (!qa) {
+            if (wide) colour_sweep_fast<false, 0, 7><<<grid, block, 0, c->stream>>>(a);
+            else      colour_sweep_fast<false, 0, 8><<<grid, block, 0, c->stream>>>(a);
+        } else if (trotter) {
+            if (wide) colour_sweep_fast<true, 1, 7><<<grid, block, 0, c->stream>>>(a);
+            else      colour_sweep_fast<true, 1, 8><<<grid, block, 0, c->stream>>>(a);
+        } else {
+            if (wide) colour_sweep_fast<true, 0, 7><<<grid, block, 0, c->stream>>>(a);
+            else      colour_sweep_fast<true, 0, 8><<<grid, block, 0, c->stream>>>(a);
+        }
         c->launches++;
         PIQMC_CUDA(cudaGetLastError());
     }

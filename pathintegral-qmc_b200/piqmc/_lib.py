@@ -9,7 +9,7 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO = os.path.join(HERE, "libpiqmc_b200.so")
+SO = os.environ.get("PIQMC_B200_LIB") or os.path.join(HERE, "libpiqmc_b200.so")
 CSRC = os.path.join(os.path.dirname(HERE), "csrc")
 
 OK, EINVAL, EZERODIV, ECUDA, ENOGRAPH, ENOSTATE, ENOMEM = 0, -1, -2, -3, -4, -5, -6
