@@ -131,6 +131,11 @@ float piqmc_jperp(double gamma, int slices, float temp);
  * Semantics are stated on the CPU in oracle/piqmc_oracle.c part 3 and reproduced bit-exactly.
  */
 int piqmc_state_alloc(piqmc_handle h, int nrows, int lanes);
+/* Turn the resident SA state (64 replicas per word) into a QA state on the device: one row per
+ * replica, every one of the `slices` lanes equal to the replica's spin -- the reference's
+ * np.tile(spinVector, (P,1)).T hand-over from the SA pre-anneal to PIQMC
+ * (examples/spinglass32.py:94-96,124-127). */
+int piqmc_state_replicas_to_slices(piqmc_handle h, int nreplicas, int slices);
 /* random initial state from Philox: tile != 0 -> one bit per (row, spin) copied to every lane
  * (the reference's np.tile(spinVector,(P,1)).T start, examples/spinglass32.py:94-96);
  * tile == 0 -> independent bit per (row*64+lane, spin). */
@@ -171,6 +176,10 @@ int piqmc_set_variant(piqmc_handle h, int variant);
 /* sa.ClassicalIsingEnergy (piqmc/sa.pyx:25-44) of every (row, lane) of the resident state,
  * float64: energies[row*lanes + lane].  energies may be NULL (result stays on the device). */
 int piqmc_energy(piqmc_handle h, double *energies);
+
+/* energies (as piqmc_energy) and packed words (as piqmc_state_download_words) in one call; the
+ * download of the words runs on a second stream and overlaps the energy reduction. */
+int piqmc_results(piqmc_handle h, double *energies, uint64_t *words);
 
 /* ClassicalIsingEnergy for host configurations: J given as nnz COO triples holding each bond
  * once (diagonal = local fields); spins[c*nspins + i] +-1; energies[c]. */

@@ -356,6 +356,8 @@ int piqmc_destroy(piqmc_handle h)
     free_dev(h->d_epart);
     free_dev(h->d_ticket);
     free_dev(h->d_stage);
+    if (h->copy_event) cudaEventDestroy(h->copy_event);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     cudaStreamDestroy(h->stream);
     delete h;
     return PIQMC_OK;
@@ -469,6 +471,7 @@ int piqmc_set_graph(piqmc_handle h, int nspins, int maxnb, const int32_t *idx, c
                       "neighbour index %d out of range at entry %zu", idx[e], e);
     if (color) TRY(check_colouring(nspins, maxnb, idx, J, ncolors, color));
     PIQMC_CUDA(cudaStreamSynchronize(h->stream));
+    const int old_nspins = h->nspins;
     free_graph(h);
 
     std::vector<float> j32(ne), j32t(ne);
@@ -504,8 +507,9 @@ int piqmc_set_graph(piqmc_handle h, int nspins, int maxnb, const int32_t *idx, c
     PIQMC_CUDA(cudaMalloc(&h->d_level, (size_t)nspins * sizeof(int32_t)));
     PIQMC_CUDA(cudaMalloc(&h->d_recs, (size_t)nspins * sizeof(PiqmcUnitRec)));
     if (color) TRY(apply_colouring(h, ncolors, color, false));
-    // a new graph invalidates any resident state
-    free_state(h);
+    // a resident state stays valid for a new graph on the same spins (words are [spin][row],
+    // whatever the couplings): the SA pre-anneal -> PIQMC hand-over may change the colouring
+    if (old_nspins != nspins) free_state(h);
     return PIQMC_OK;
 }
 
@@ -694,6 +698,32 @@ int piqmc_state_alloc(piqmc_handle h, int nrows, int lanes)
     return PIQMC_OK;
 }
 
+int piqmc_state_replicas_to_slices(piqmc_handle h, int nreplicas, int slices)
+{
+    USE(h);
+    PIQMC_REQUIRE(h->d_words && h->lanes == 64, PIQMC_ENOSTATE, "no resident SA state (64 replicas per word)");
+    PIQMC_REQUIRE(nreplicas > 0 && nreplicas <= h->nrows * 64 && nreplicas <= 65535, PIQMC_EINVAL,
+                  "nreplicas must be in [1, min(64*rows, 65535)]");
+    PIQMC_REQUIRE(slices >= 2 && slices <= 64, PIQMC_EINVAL, "slices must be in [2, 64]");
+    uint64_t *src = h->d_words;
+    const int src_rows = h->nrows;
+    uint64_t *dst = nullptr;
+    PIQMC_CUDA(cudaMalloc(&dst, (size_t)nreplicas * h->nspins * sizeof(uint64_t)));
+    int rc = launch_replicas_to_slices(h, src, src_rows, dst, nreplicas, slices);
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    if (rc != PIQMC_OK || e != cudaSuccess) {
+        cudaFree(dst);
+        if (rc == PIQMC_OK) piqmc_set_error("replicas_to_slices failed: %s", cudaGetErrorString(e));
+        return rc != PIQMC_OK ? rc : PIQMC_ECUDA;
+    }
+    free_state(h);
+    h->d_words = dst;
+    PIQMC_CUDA(cudaMalloc(&h->d_energy, (size_t)nreplicas * slices * sizeof(double)));
+    h->nrows = nreplicas;
+    h->lanes = slices;
+    return PIQMC_OK;
+}
+
 int piqmc_state_init_random(piqmc_handle h, uint64_t seed, uint32_t row0, int tile)
 {
     USE(h);
@@ -798,6 +828,26 @@ int piqmc_energy(piqmc_handle h, double *energies)
                                    cudaMemcpyDeviceToHost, h->stream));
         PIQMC_CUDA(cudaStreamSynchronize(h->stream));
     }
+    return PIQMC_OK;
+}
+
+int piqmc_results(piqmc_handle h, double *energies, uint64_t *words)
+{
+    USE(h);
+    PIQMC_REQUIRE(h->d_words, PIQMC_ENOSTATE, "no packed state (call piqmc_state_alloc)");
+    PIQMC_REQUIRE(energies && words, PIQMC_EINVAL, "null output");
+    if (!h->copy_stream) PIQMC_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    if (!h->copy_event) PIQMC_CUDA(cudaEventCreateWithFlags(&h->copy_event, cudaEventDisableTiming));
+    // the download of the packed state (second stream) overlaps the energy reduction
+    PIQMC_CUDA(cudaEventRecord(h->copy_event, h->stream));
+    PIQMC_CUDA(cudaStreamWaitEvent(h->copy_stream, h->copy_event, 0));
+    PIQMC_CUDA(cudaMemcpyAsync(words, h->d_words, (size_t)h->nrows * h->nspins * sizeof(uint64_t),
+                               cudaMemcpyDeviceToHost, h->copy_stream));
+    TRY(launch_energy(h));
+    PIQMC_CUDA(cudaMemcpyAsync(energies, h->d_energy, (size_t)h->nrows * h->lanes * sizeof(double),
+                               cudaMemcpyDeviceToHost, h->stream));
+    PIQMC_CUDA(cudaStreamSynchronize(h->stream));
+    PIQMC_CUDA(cudaStreamSynchronize(h->copy_stream));
     return PIQMC_OK;
 }
 

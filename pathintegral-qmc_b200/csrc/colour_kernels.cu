@@ -145,7 +145,31 @@ __global__ void pack_spins_kernel(uint64_t *words, const int8_t *spins, int nspi
     words[tid] = w;
 }
 
+// SA state (64 replicas per word) -> QA state (one row per replica, every slice = the replica's
+// spin): the reference's np.tile(spinVector, (P,1)).T start (examples/spinglass32.py:94-96) without
+// a trip through the host.
+__global__ void replicas_to_slices_kernel(const uint64_t *__restrict__ src, uint64_t *__restrict__ dst,
+                                          int nspins, int src_rows, int dst_rows, int lanes)
+{
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (size_t)dst_rows * nspins) return;
+    const size_t r = tid % dst_rows, i = tid / dst_rows;
+    const uint64_t bit = (src[i * src_rows + (r >> 6)] >> (r & 63)) & 1ull;
+    dst[tid] = bit ? ((lanes == 64) ? ~0ull : ((1ull << lanes) - 1ull)) : 0ull;
+}
+
 }  // namespace
+
+int launch_replicas_to_slices(piqmc_ctx *c, const uint64_t *d_src, int src_rows, uint64_t *d_dst, int dst_rows,
+                              int lanes)
+{
+    const size_t n = (size_t)dst_rows * c->nspins;
+    replicas_to_slices_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(d_src, d_dst, c->nspins, src_rows,
+                                                                                dst_rows, lanes);
+    c->launches++;
+    PIQMC_CUDA(cudaGetLastError());
+    return PIQMC_OK;
+}
 
 int launch_state_init(piqmc_ctx *c, uint64_t seed, uint32_t row0, int tile)
 {

@@ -50,6 +50,8 @@ struct piqmc_ctx {
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // second stream: result download overlapping the energy reduction
+    cudaEvent_t copy_event = nullptr;
     uint64_t launches = 0;
 
     // graph (set by piqmc_set_graph)
@@ -148,6 +150,8 @@ int launch_sa_multispin_det(piqmc_ctx *c, const float *d_temps, int nsched, int 
 
 int launch_state_init(piqmc_ctx *c, uint64_t seed, uint32_t row0, int tile);
 int launch_pack_spins(piqmc_ctx *c, const int8_t *d_spins, int tile);
+int launch_replicas_to_slices(piqmc_ctx *c, const uint64_t *d_src, int src_rows, uint64_t *d_dst, int dst_rows,
+                              int lanes);
 // one colour class (device list `members`) of one sweep; qa != 0: QA rules (jp2 = 2*jperp)
 int launch_colour_sweep(piqmc_ctx *c, int qa, int trotter, const int32_t *members, int nmem, float jp2,
                         float invT, uint64_t seed, uint32_t row0, uint32_t sweep);

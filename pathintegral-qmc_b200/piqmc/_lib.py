@@ -54,6 +54,7 @@ SIGNATURES = {
     "piqmc_sa_multispin_det": (c_int, [c_void, c_void, c_int, c_int, c_int, c_void, c_void, c_void]),
     "piqmc_jperp": (c_f, [c_d, c_int, c_f]),
     "piqmc_state_alloc": (c_int, [c_void, c_int, c_int]),
+    "piqmc_state_replicas_to_slices": (c_int, [c_void, c_int, c_int]),
     "piqmc_state_init_random": (c_int, [c_void, c_u64, c_u32, c_int]),
     "piqmc_state_upload_spins": (c_int, [c_void, c_void, c_int]),
     "piqmc_state_upload_words": (c_int, [c_void, c_void]),
@@ -65,6 +66,7 @@ SIGNATURES = {
     "piqmc_set_variant": (c_int, [c_void, c_int]),
     "piqmc_set_global_moves": (c_int, [c_void, c_int]),
     "piqmc_energy": (c_int, [c_void, c_void]),
+    "piqmc_results": (c_int, [c_void, c_void, c_void]),
     "piqmc_energy_coo": (c_int, [c_void, c_int, c_int, c_void, c_void, c_void, c_int, c_void, c_void]),
 }
 

@@ -110,8 +110,9 @@ class Device:
         if col is not None and col.shape != (idx.shape[0],):
             raise ValueError("color must have one entry per spin")
         check(lib.piqmc_set_graph(self._h, idx.shape[0], idx.shape[1], _ptr(idx), _ptr(J), ncol, _ptr(col)))
+        if idx.shape[0] != self.nspins:             # the library keeps a state on the same spins
+            self.nrows = self.lanes = 0
         self.nspins, self.maxnb, self.ncolors = idx.shape[0], idx.shape[1], ncol
-        self.nrows = self.lanes = 0
         self._graph_key = key
 
     # ------------------------------------------------------------------ deterministic paths
@@ -181,6 +182,12 @@ class Device:
     def state_alloc(self, nrows, lanes):
         check(lib.piqmc_state_alloc(self._h, int(nrows), int(lanes)))
         self.nrows, self.lanes = int(nrows), int(lanes)
+
+    def state_replicas_to_slices(self, nreplicas, slices):
+        """SA state (64 replicas per word) -> QA state (row per replica, all slices = its spin),
+        on the device."""
+        check(lib.piqmc_state_replicas_to_slices(self._h, int(nreplicas), int(slices)))
+        self.nrows, self.lanes = int(nreplicas), int(slices)
 
     def state_init_random(self, seed, row0=0, tile=True):
         check(lib.piqmc_state_init_random(self._h, int(seed), int(row0), 1 if tile else 0))
@@ -268,6 +275,18 @@ class Device:
         out = np.empty((self.nrows, self.lanes), dtype=np.float64)
         check(lib.piqmc_energy(self._h, _ptr(out)))
         return out
+
+    def results(self, words_out=None):
+        """(energies float64[nrows, lanes], words uint64 view [nrows, nspins]) in one call; the
+        state download overlaps the energy reduction."""
+        en = np.empty((self.nrows, self.lanes), dtype=np.float64)
+        if words_out is None:
+            words_out = np.empty((self.nspins, self.nrows), dtype=np.uint64)
+        elif (words_out.dtype != np.uint64 or not words_out.flags.c_contiguous
+              or words_out.shape != (self.nspins, self.nrows)):
+            raise ValueError("words_out must be C-contiguous uint64[nspins, nrows]")
+        check(lib.piqmc_results(self._h, _ptr(en), _ptr(words_out)))
+        return en, words_out.T
 
     def energy_coo(self, nspins, row, col, val, spins):
         row = np.ascontiguousarray(row, dtype=np.int32)

@@ -119,7 +119,8 @@ def QuantumAnnealReplicas(sched, mcsteps, slices, temp, nspins, spins0, nbs, see
     global_moves: also attempt a world-line move (flip the spin in all slices at once) after the
         local moves of every spin -- not in the reference; off by default.
 
-    spins0: int8[R, nspins] copied to every slice (tile=True, the reference's
+    spins0: "resident" = take the replicas of the SA state resident on the device (after
+            sa.AnnealReplicas(..., download=False); give nreplicas), or int8[R, nspins] copied to every slice (tile=True, the reference's
             np.tile(spinVector, (P,1)).T start), or int8[R, slices, nspins] (tile=False), or None
             for a Philox-generated random start (give nreplicas).
     words_out: optional C-contiguous uint64[nspins, R] host buffer (e.g. device.pinned_empty) that
@@ -140,10 +141,14 @@ def QuantumAnnealReplicas(sched, mcsteps, slices, temp, nspins, spins0, nbs, see
     d.set_graph(nbs, color)
     if int(nspins) != d.nspins:
         raise ValueError("nspins=%d but nbs describes %d spins" % (nspins, d.nspins))
-    R = int(nreplicas) if spins0 is None else int(np.asarray(spins0).shape[0])
-    d.state_alloc(R, slices)
+    resident = isinstance(spins0, str) and spins0 == "resident"
+    R = int(nreplicas) if (spins0 is None or resident) else int(np.asarray(spins0).shape[0])
+    if not resident:
+        d.state_alloc(R, slices)
     t.append(time.perf_counter())
-    if spins0 is None:
+    if resident:
+        d.state_replicas_to_slices(R, slices)
+    elif spins0 is None:
         d.state_init_random(seed, replica0, tile=True)
     else:
         d.state_upload_spins(spins0, tile=tile)
@@ -156,13 +161,17 @@ def QuantumAnnealReplicas(sched, mcsteps, slices, temp, nspins, spins0, nbs, see
         d.set_global_moves(False)
     t.append(time.perf_counter())
     out = {"energies": None, "words": None}
-    if energies:
-        out["energies"] = d.energy(download=download)
-    t.append(time.perf_counter())
-    if download:
-        out["words"] = d.state_download_words(out=words_out)
+    if energies and download:
+        out["energies"], out["words"] = d.results(words_out)
+        t.append(time.perf_counter())
     else:
-        d.synchronize()
+        if energies:
+            out["energies"] = d.energy(download=download)
+        t.append(time.perf_counter())
+        if download:
+            out["words"] = d.state_download_words(out=words_out)
+        else:
+            d.synchronize()
     t.append(time.perf_counter())
     out["seconds"] = dict(zip(("graph+alloc", "upload", "sweeps", "energy", "download"), np.diff(t).tolist()))
     return out

@@ -182,7 +182,7 @@ def _resolve_order(order, nbs, nsweeps, nspins, order_seed):
 
 
 def AnnealReplicas(sched, mcsteps, spins0, nbs, seed, order="permutation", color=None, row0=0,
-                   device=None, energies=True, nreplicas=None):
+                   device=None, energies=True, nreplicas=None, download=True):
     """Production SA: R independent replicas, 64 per uint64 word, colour-class Metropolis with
     Philox4x32-10 uniforms keyed by (seed; spin, replica, sweep).  sa.Anneal rules (float32 local
     field in table order, `>= 0` shortcut, temperature schedule).
@@ -195,6 +195,8 @@ def AnnealReplicas(sched, mcsteps, spins0, nbs, seed, order="permutation", color
         int32[N] / int32[nsweeps,N]  explicit visiting order(s).
     color: explicit colour classes (overrides order).
     spins0: int8[R,N] (+-1) or None for a Philox-generated random start (then give nreplicas).
+    download=False leaves the result on the device only (for qmc.QuantumAnnealReplicas(spins0=
+    "resident"), the SA pre-anneal -> PIQMC hand-over of examples/spinglass32.py:124-127).
     Returns dict(spins=int8[R,N], energies=float64[R] or None, words=uint64[G,N])."""
     sched = np.ascontiguousarray(sched, dtype=np.float64)
     d = device or _dev.default_device()
@@ -216,6 +218,9 @@ def AnnealReplicas(sched, mcsteps, spins0, nbs, seed, order="permutation", color
         d.state_upload_spins(s.reshape(G, 64, n), tile=False)
     d.sa_colour(sched, int(mcsteps), seed, row0=row0, orders=orders)
     en = d.energy().reshape(-1)[:R] if energies else None
+    if not download:
+        d.synchronize()
+        return {"spins": None, "energies": en, "words": None}
     words = d.state_download_words()
     spins = _tools.UnpackWords(words, 64).reshape(G * 64, n)[:R]
     return {"spins": spins, "energies": en, "words": words}

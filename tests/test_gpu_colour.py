@@ -11,6 +11,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle as O
+import piqmc.tools as tools
 from helpers import GS_ENERGY, NSPINS, ks_2samp_p
 from test_oracle import _J
 
@@ -151,6 +152,41 @@ def test_sa_colour_random_start_matches_oracle_init(dev):
     O.sa_colour(sched, 1, idx, J32, color, want, seed=5)
     out = sa.AnnealReplicas(sched, 1, None, nbs, 5, color=color, nreplicas=R, device=dev)
     assert np.array_equal(out["spins"], want)
+
+
+@pytest.mark.parametrize("R,P", [(100, 20), (64, 64), (7, 5)])
+def test_resident_handover_sa_to_qa_and_results(dev, R, P):
+    """SA pre-anneal -> PIQMC hand-over on the device (examples/spinglass32.py:124-127, np.tile of
+    the annealed vector over the slices) == download + tiled upload through the host; results()
+    (energies + words in one call) == energy() + state_download_words()."""
+    import piqmc.qmc as qmc
+    import piqmc.sa as sa
+    nbs, idx, J32, color = _torus(8, 3)
+    ssched, qsched = np.linspace(3.0, 0.01, 6), np.linspace(1.5, 1e-8, 5)
+    pre = sa.AnnealReplicas(ssched, 1, None, nbs, 11, color=color, nreplicas=R, device=dev)
+    host = qmc.QuantumAnnealReplicas(qsched, 1, P, 0.01, 64, pre["spins"], nbs, 12, color=color, device=dev)
+    # the pre-anneal runs under another colouring (fresh permutation per sweep): the resident state
+    # survives the change of colouring
+    pre2 = sa.AnnealReplicas(ssched, 1, None, nbs, 11, order="permutation", nreplicas=R, device=dev)
+    host2 = qmc.QuantumAnnealReplicas(qsched, 1, P, 0.01, 64, pre2["spins"], nbs, 12, color=color, device=dev)
+    sa.AnnealReplicas(ssched, 1, None, nbs, 11, order="permutation", nreplicas=R, device=dev, download=False)
+    res2 = qmc.QuantumAnnealReplicas(qsched, 1, P, 0.01, 64, "resident", nbs, 12, color=color, nreplicas=R,
+                                     device=dev)
+    assert np.array_equal(res2["words"], host2["words"])
+    sa.AnnealReplicas(ssched, 1, None, nbs, 11, color=color, nreplicas=R, device=dev, download=False)
+    res = qmc.QuantumAnnealReplicas(qsched, 1, P, 0.01, 64, "resident", nbs, 12, color=color, nreplicas=R,
+                                    device=dev)
+    assert np.array_equal(res["words"], host["words"])
+    assert np.array_equal(res["energies"], host["energies"])
+    # the separate calls agree with the combined one
+    assert np.array_equal(dev.energy(), res["energies"])
+    assert np.array_equal(dev.state_download_words(), res["words"])
+    # and with the CPU statement of the whole chain
+    want = pre["spins"].copy()
+    ref = np.repeat(want[:, :, None], P, axis=2).copy()
+    O.qa_colour(qsched, 1, P, 0.01, idx, J32, color, ref, 12)
+    got = np.transpose(tools.UnpackWords(res["words"], P), (0, 2, 1))
+    assert np.array_equal(got, ref)
 
 
 # ------------------------------------------------------------------- order-equivalent colourings
