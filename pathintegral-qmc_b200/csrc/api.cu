@@ -111,7 +111,12 @@ static void bucket_members(int nspins, int ncolors, const int32_t *color, std::v
     for (int i = 0; i < nspins; i++) members[fill[color[i]]++] = i;
 }
 
-// unit records (dataflow kernel) for the members listed in `order`, given the level of every spin
+// unit records (dataflow kernel) for the members listed in `order`, given the level of every spin.
+// The (up to 4) table columns of a spin are stored sorted by |J| descending (stable); `pad` keeps
+// the original column of every sorted entry (2 bits each) and the sign bits (J < 0) in bits 8..11:
+// in the sorted, sign-normalised variables the Metropolis decision of every Trotter class is a
+// *regular* monotone function -- one of only 27 -- which the kernel evaluates by name
+// (colour_fast.cu).  The energies themselves are still summed in table order.
 static void build_unit_recs(const piqmc_ctx *h, const int32_t *level, const int32_t *order,
                             const int32_t *sweepoff, PiqmcUnitRec *out)
 {
@@ -121,18 +126,32 @@ static void build_unit_recs(const piqmc_ctx *h, const int32_t *level, const int3
         PiqmcUnitRec &r = out[k];
         r.spin = i;
         r.sweepoff = sweepoff ? sweepoff[k] : 0;
-        r.pad = 0;
+        int32_t nb[4];
+        float J[4];
+        uint8_t dep[4];
         for (int n = 0; n < 4; n++) {
-            r.nb[n] = i;
-            r.J[n] = 0.0f;
-            r.dep[n] = 0;
+            nb[n] = i;
+            J[n] = 0.0f;
+            dep[n] = 0;
             if (n < mb) {
                 const size_t e = (size_t)i * h->maxnb + n;
-                r.nb[n] = h->h_idx[e];
-                r.J[n] = h->h_J32[e];
-                if (h->h_live[e]) r.dep[n] = level[h->h_idx[e]] < level[i] ? 2 : 1;
+                nb[n] = h->h_idx[e];
+                J[n] = h->h_J32[e];
+                if (h->h_live[e]) dep[n] = level[h->h_idx[e]] < level[i] ? 2 : 1;
             }
         }
+        int col[4] = {0, 1, 2, 3};
+        std::stable_sort(col, col + 4, [&](int a, int b) { return fabsf(J[a]) > fabsf(J[b]); });
+        int32_t pad = 0;
+        for (int z = 0; z < 4; z++) {
+            const int n = col[z];
+            r.nb[z] = nb[n];
+            r.J[z] = J[n];
+            r.dep[z] = dep[n];
+            pad |= n << (2 * z);
+            if (J[n] < 0.0f) pad |= 1 << (8 + z);
+        }
+        r.pad = pad;
     }
 }
 

@@ -35,11 +35,12 @@ void piqmc_set_error(const char *fmt, ...);
 struct alignas(16) PiqmcUnitRec {
     int32_t spin;
     int32_t sweepoff;     // sweep lag of this member in the period-major order (0 for per-sweep lists)
-    int32_t nb[4];        // neighbour spins (== spin for self entries and unused columns)
-    float J[4];           // couplings (0 for unused columns)
+    int32_t nb[4];        // neighbour spins (== spin for self entries and unused columns),
+                          // table columns sorted by |J| descending
+    float J[4];           // couplings (0 for unused columns), same order
     uint8_t dep[4];       // 0: nothing to wait for; 1: neighbour of a higher level (its previous sweep);
                           // 2: neighbour of a lower level (its current sweep)
-    int32_t pad;
+    int32_t pad;          // bits 2z..2z+1: table column of sorted entry z; bit 8+z: J[z] < 0
 };
 static_assert(sizeof(PiqmcUnitRec) == 48, "PiqmcUnitRec must be 48 bytes");
 
