@@ -116,6 +116,20 @@ int piqmc_sa_det(piqmc_handle h, const double *sched, int nsched, int mcsteps, i
                  int8_t *spins, const int32_t *perms, piqmc_rand_state *rstate,
                  const double *uniforms, uint64_t nuniforms, uint64_t *consumed);
 
+/* qmc.QuantumAnneal_dense (piqmc/qmc.pyx:141-242) and sa.Anneal_dense (piqmc/sa.pyx:126-187): the
+ * same sweeps with a dense coupling matrix J[nspins*nspins] (float64, row-major; only the upper
+ * triangle and the diagonal -- the local fields -- are read, as in the reference).  No graph has
+ * to be set.  Couplings stay float64 (the sparse variants narrow them to float); Anneal_dense
+ * accepts on ediff > 0 where sa.Anneal accepts on >= 0.  Other arguments as above. */
+int piqmc_qa_dense_det(piqmc_handle h, int nspins, const double *J, const double *sched, int nsched,
+                       int mcsteps, int slices, float temp, int nreplicas, int8_t *spins,
+                       const int32_t *perms, piqmc_rand_state *rstate, const double *uniforms,
+                       uint64_t nuniforms, uint64_t *consumed);
+int piqmc_sa_dense_det(piqmc_handle h, int nspins, const double *J, const double *sched, int nsched,
+                       int mcsteps, int nreplicas, int8_t *spins, const int32_t *perms,
+                       piqmc_rand_state *rstate, const double *uniforms, uint64_t nuniforms,
+                       uint64_t *consumed);
+
 /* sa.Anneal_multispin (piqmc/sa.pyx:282-405): groups of 64 replicas, float64 ediffs, no
  * ediff>0 shortcut.  words[g*nspins + i]: replica k of group g in bit 63-k (sa.pyx:339-345).
  * rands[((g*nsweeps + sweep)*nspins + t)*64 + k]: the rng.rand(64) block in force at attempt t. */

@@ -49,6 +49,13 @@ def lib():
         L.oracle_sa_reference.restype = ctypes.c_uint64
         L.oracle_sa_reference.argtypes = [c_dp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                           c_dp, ctypes.c_long, c_dp, ctypes.c_int, c_ip] + usrc
+        L.oracle_qa_dense.restype = ctypes.c_uint64
+        L.oracle_qa_dense.argtypes = [c_dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                      ctypes.c_int, c_dp, ctypes.c_long, ctypes.c_long,
+                                      c_dp, ctypes.c_long, ctypes.c_long, c_ip] + usrc
+        L.oracle_sa_dense.restype = ctypes.c_uint64
+        L.oracle_sa_dense.argtypes = [c_dp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                      c_dp, ctypes.c_long, c_dp, ctypes.c_long, ctypes.c_long, c_ip] + usrc
         L.oracle_qa_parallel1.restype = ctypes.c_uint64
         L.oracle_qa_parallel1.argtypes = [c_dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                           ctypes.c_int, c_dp, ctypes.c_long, ctypes.c_long,
@@ -158,6 +165,32 @@ def sa_reference(sched, mcsteps, svec, nbs, perms, uniforms=None, gstate=None):
     return lib().oracle_sa_reference(_p(sched, c_dp), sched.size, mcsteps, svec.size,
                                      _p(svec, c_dp), svec.strides[0] // 8, _p(nbs, c_dp), nbs.shape[1],
                                      _p(perms, c_ip), kind, tab, ntab, g)
+
+
+def qa_dense(sched, mcsteps, slices, temp, nspins, confs, J, perms, uniforms=None, gstate=None):
+    """qmc.QuantumAnneal_dense (qmc.pyx:141-242), in place on confs float64[N,P]; J float64[N,N]."""
+    sched = np.ascontiguousarray(sched, dtype=np.float64)
+    J = np.asarray(J, dtype=np.float64)
+    perms = np.ascontiguousarray(perms, dtype=np.int32)
+    assert confs.dtype == np.float64 and confs.shape == (nspins, slices) and J.shape == (nspins, nspins)
+    assert perms.shape == (sched.size * mcsteps, nspins)
+    kind, keep, tab, ntab, g = _usrc(uniforms, gstate)
+    return lib().oracle_qa_dense(_p(sched, c_dp), sched.size, mcsteps, slices, ctypes.c_float(temp),
+                                 nspins, _p(confs, c_dp), confs.strides[0] // 8, confs.strides[1] // 8,
+                                 _p(J, c_dp), J.strides[0] // 8, J.strides[1] // 8, _p(perms, c_ip),
+                                 kind, tab, ntab, g)
+
+
+def sa_dense(sched, mcsteps, svec, J, perms, uniforms=None, gstate=None):
+    """sa.Anneal_dense (sa.pyx:126-187), in place on svec float64[N]; J float64[N,N]."""
+    sched = np.ascontiguousarray(sched, dtype=np.float64)
+    J = np.asarray(J, dtype=np.float64)
+    perms = np.ascontiguousarray(perms, dtype=np.int32)
+    assert svec.dtype == np.float64 and svec.ndim == 1 and J.shape == (svec.size, svec.size)
+    kind, keep, tab, ntab, g = _usrc(uniforms, gstate)
+    return lib().oracle_sa_dense(_p(sched, c_dp), sched.size, mcsteps, svec.size,
+                                 _p(svec, c_dp), svec.strides[0] // 8, _p(J, c_dp), J.strides[0] // 8,
+                                 J.strides[1] // 8, _p(perms, c_ip), kind, tab, ntab, g)
 
 
 def qa_parallel1(sched, mcsteps, slices, temp, nspins, confs, nbs, uniforms=None, gstate=None):

@@ -558,25 +558,32 @@ int piqmc_order_levels(int nspins, int maxnb, const int32_t *idx, const double *
 // ---- deterministic paths ---------------------------------------------------------------------
 static int det_common_checks(piqmc_handle h, const double *sched, int nsched, int mcsteps, int nreplicas,
                              const void *spins, const int32_t *perms, const piqmc_rand_state *rstate,
-                             const double *uniforms)
+                             const double *uniforms, const double *dense = nullptr, int dense_n = 0)
 {
-    PIQMC_REQUIRE(h->nspins > 0, PIQMC_ENOGRAPH, "piqmc_set_graph has not been called");
+    if (dense) PIQMC_REQUIRE(dense_n > 0, PIQMC_EINVAL, "nspins must be positive");
+    else PIQMC_REQUIRE(h->nspins > 0, PIQMC_ENOGRAPH, "piqmc_set_graph has not been called");
     PIQMC_REQUIRE(sched && nsched >= 0 && mcsteps >= 0 && nreplicas > 0 && spins && perms, PIQMC_EINVAL,
                   "bad arguments");
     PIQMC_REQUIRE(rstate || uniforms, PIQMC_EINVAL, "need either rstate or uniforms");
     return PIQMC_OK;
 }
 
-int piqmc_qa_det(piqmc_handle h, const double *sched, int nsched, int mcsteps, int slices, float temp,
-                 int nreplicas, int8_t *spins, const int32_t *perms, piqmc_rand_state *rstate,
-                 const double *uniforms, uint64_t nuniforms, uint64_t *consumed)
+static int qa_det_impl(piqmc_handle h, const double *sched, int nsched, int mcsteps, int slices, float temp,
+                       int nreplicas, int8_t *spins, const int32_t *perms, piqmc_rand_state *rstate,
+                       const double *uniforms, uint64_t nuniforms, uint64_t *consumed, const double *dense,
+                       int dense_n)
 {
     USE(h);
-    TRY(det_common_checks(h, sched, nsched, mcsteps, nreplicas, spins, perms, rstate, uniforms));
+    TRY(det_common_checks(h, sched, nsched, mcsteps, nreplicas, spins, perms, rstate, uniforms, dense, dense_n));
     PIQMC_REQUIRE(slices >= 2, PIQMC_EINVAL, "slices must be >= 2 (the reference reads slice 1)");
     // ZeroDivisionError conditions of piqmc/qmc.c:2065-2074 and :2407-2416
     PIQMC_REQUIRE((float)slices * temp != 0.0f && temp != 0.0f, PIQMC_EZERODIV, "float division");
-    const int N = h->nspins;
+    const int N = dense ? dense_n : h->nspins;
+    DevBuf<double> d_dense;
+    if (dense) {
+        PIQMC_CUDA(d_dense.alloc((size_t)N * N));
+        PIQMC_CUDA(cudaMemcpyAsync(d_dense.p, dense, (size_t)N * N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    }
     const size_t nsweeps = (size_t)nsched * mcsteps;
     std::vector<float> jperp(std::max(nsched, 1));
     for (int f = 0; f < nsched; f++) jperp[f] = piqmc_jperp(sched[f], slices, temp);
@@ -605,7 +612,8 @@ int piqmc_qa_det(piqmc_handle h, const double *sched, int nsched, int mcsteps, i
                                    cudaMemcpyHostToDevice, h->stream));
     }
     TRY(launch_qa_det(h, d_jperp.p, nsched, mcsteps, slices, temp, nreplicas, d_spins.p, d_perms.p,
-                      uniforms ? nullptr : d_rs.p, uniforms ? d_uni.p : nullptr, nuniforms, d_cons.p));
+                      uniforms ? nullptr : d_rs.p, uniforms ? d_uni.p : nullptr, nuniforms, d_cons.p,
+                      dense ? d_dense.p : nullptr, N));
     PIQMC_CUDA(cudaMemcpyAsync(spins, d_spins.p, nsp, cudaMemcpyDeviceToHost, h->stream));
     if (!uniforms)
         PIQMC_CUDA(cudaMemcpyAsync(rstate, d_rs.p, (size_t)nreplicas * sizeof(piqmc_rand_state),
@@ -617,13 +625,18 @@ int piqmc_qa_det(piqmc_handle h, const double *sched, int nsched, int mcsteps, i
     return PIQMC_OK;
 }
 
-int piqmc_sa_det(piqmc_handle h, const double *sched, int nsched, int mcsteps, int nreplicas,
-                 int8_t *spins, const int32_t *perms, piqmc_rand_state *rstate, const double *uniforms,
-                 uint64_t nuniforms, uint64_t *consumed)
+static int sa_det_impl(piqmc_handle h, const double *sched, int nsched, int mcsteps, int nreplicas,
+                       int8_t *spins, const int32_t *perms, piqmc_rand_state *rstate, const double *uniforms,
+                       uint64_t nuniforms, uint64_t *consumed, const double *dense, int dense_n)
 {
     USE(h);
-    TRY(det_common_checks(h, sched, nsched, mcsteps, nreplicas, spins, perms, rstate, uniforms));
-    const int N = h->nspins;
+    TRY(det_common_checks(h, sched, nsched, mcsteps, nreplicas, spins, perms, rstate, uniforms, dense, dense_n));
+    const int N = dense ? dense_n : h->nspins;
+    DevBuf<double> d_dense;
+    if (dense) {
+        PIQMC_CUDA(d_dense.alloc((size_t)N * N));
+        PIQMC_CUDA(cudaMemcpyAsync(d_dense.p, dense, (size_t)N * N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    }
     const size_t nsweeps = (size_t)nsched * mcsteps;
     std::vector<float> temps(std::max(nsched, 1));
     for (int t = 0; t < nsched; t++) temps[t] = (float)sched[t];      // sa.pyx:96
@@ -652,7 +665,8 @@ int piqmc_sa_det(piqmc_handle h, const double *sched, int nsched, int mcsteps, i
                                    cudaMemcpyHostToDevice, h->stream));
     }
     TRY(launch_sa_det(h, d_temps.p, nsched, mcsteps, nreplicas, d_spins.p, d_perms.p,
-                      uniforms ? nullptr : d_rs.p, uniforms ? d_uni.p : nullptr, nuniforms, d_cons.p));
+                      uniforms ? nullptr : d_rs.p, uniforms ? d_uni.p : nullptr, nuniforms, d_cons.p,
+                      dense ? d_dense.p : nullptr, N));
     PIQMC_CUDA(cudaMemcpyAsync(spins, d_spins.p, nsp, cudaMemcpyDeviceToHost, h->stream));
     if (!uniforms)
         PIQMC_CUDA(cudaMemcpyAsync(rstate, d_rs.p, (size_t)nreplicas * sizeof(piqmc_rand_state),
@@ -662,6 +676,40 @@ int piqmc_sa_det(piqmc_handle h, const double *sched, int nsched, int mcsteps, i
                                    cudaMemcpyDeviceToHost, h->stream));
     PIQMC_CUDA(cudaStreamSynchronize(h->stream));
     return PIQMC_OK;
+}
+
+int piqmc_qa_det(piqmc_handle h, const double *sched, int nsched, int mcsteps, int slices, float temp,
+                 int nreplicas, int8_t *spins, const int32_t *perms, piqmc_rand_state *rstate,
+                 const double *uniforms, uint64_t nuniforms, uint64_t *consumed)
+{
+    return qa_det_impl(h, sched, nsched, mcsteps, slices, temp, nreplicas, spins, perms, rstate, uniforms,
+                       nuniforms, consumed, nullptr, 0);
+}
+
+int piqmc_sa_det(piqmc_handle h, const double *sched, int nsched, int mcsteps, int nreplicas,
+                 int8_t *spins, const int32_t *perms, piqmc_rand_state *rstate, const double *uniforms,
+                 uint64_t nuniforms, uint64_t *consumed)
+{
+    return sa_det_impl(h, sched, nsched, mcsteps, nreplicas, spins, perms, rstate, uniforms, nuniforms, consumed,
+                       nullptr, 0);
+}
+
+int piqmc_qa_dense_det(piqmc_handle h, int nspins, const double *J, const double *sched, int nsched, int mcsteps,
+                       int slices, float temp, int nreplicas, int8_t *spins, const int32_t *perms,
+                       piqmc_rand_state *rstate, const double *uniforms, uint64_t nuniforms, uint64_t *consumed)
+{
+    PIQMC_REQUIRE(J != nullptr, PIQMC_EINVAL, "null coupling matrix");
+    return qa_det_impl(h, sched, nsched, mcsteps, slices, temp, nreplicas, spins, perms, rstate, uniforms,
+                       nuniforms, consumed, J, nspins);
+}
+
+int piqmc_sa_dense_det(piqmc_handle h, int nspins, const double *J, const double *sched, int nsched, int mcsteps,
+                       int nreplicas, int8_t *spins, const int32_t *perms, piqmc_rand_state *rstate,
+                       const double *uniforms, uint64_t nuniforms, uint64_t *consumed)
+{
+    PIQMC_REQUIRE(J != nullptr, PIQMC_EINVAL, "null coupling matrix");
+    return sa_det_impl(h, sched, nsched, mcsteps, nreplicas, spins, perms, rstate, uniforms, nuniforms, consumed,
+                       J, nspins);
 }
 
 int piqmc_sa_multispin_det(piqmc_handle h, const double *sched, int nsched, int mcsteps, int ngroups,

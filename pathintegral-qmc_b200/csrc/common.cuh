@@ -142,10 +142,12 @@ __device__ __forceinline__ uint32_t colour_thresh(float x)
 // ------------------------------------------------------------------------------------------
 int launch_qa_det(piqmc_ctx *c, const float *d_jperp, int nsched, int mcsteps, int slices, float temp,
                   int nreplicas, int8_t *d_spins, const int32_t *d_perms, piqmc_rand_state *d_rstate,
-                  const double *d_uniforms, uint64_t nuniforms, unsigned long long *d_consumed);
+                  const double *d_uniforms, uint64_t nuniforms, unsigned long long *d_consumed,
+                  const double *d_dense = nullptr, int dense_n = 0);
 int launch_sa_det(piqmc_ctx *c, const float *d_temps, int nsched, int mcsteps, int nreplicas,
                   int8_t *d_spins, const int32_t *d_perms, piqmc_rand_state *d_rstate,
-                  const double *d_uniforms, uint64_t nuniforms, unsigned long long *d_consumed);
+                  const double *d_uniforms, uint64_t nuniforms, unsigned long long *d_consumed,
+                  const double *d_dense = nullptr, int dense_n = 0);
 int launch_sa_multispin_det(piqmc_ctx *c, const float *d_temps, int nsched, int mcsteps, int ngroups,
                             uint64_t *d_words, const int32_t *d_perms, const double *d_rands);
 

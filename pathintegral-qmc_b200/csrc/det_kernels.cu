@@ -63,10 +63,21 @@ __device__ __forceinline__ float signed_term(float jv, int neg)
     return neg ? -t : t;
 }
 
-// qmc.QuantumAnneal, piqmc/qmc.pyx:76-136.
+// one dense term added to the float running sum the way the generated C does it (double add, then
+// narrowing): ediff = (float)(ediff + (-2.0*s_i) * (J*s_j)); the products are exact for s = +-1.
+__device__ __forceinline__ float dense_add(float ediff, double jv, int prod)
+{
+    const double t = __dmul_rn(prod < 0 ? 2.0 : -2.0, jv);
+    return __double2float_rn(__dadd_rn((double)ediff, t));
+}
+
+// qmc.QuantumAnneal, piqmc/qmc.pyx:76-136; DENSE: qmc.QuantumAnneal_dense, piqmc/qmc.pyx:141-242
+// (coupling matrix Jd[N][N] float64, upper triangle + diagonal read, couplings not narrowed).
+template <bool DENSE>
 __global__ void __launch_bounds__(32) qa_det_kernel(
     const float *__restrict__ jperp_tab, int nsched, int mcsteps, int slices, float temp,
     int nspins, int maxnb, const int32_t *__restrict__ idx, const float *__restrict__ J,
+    const double *__restrict__ Jd,
     int nreplicas, int8_t *__restrict__ spins, const int32_t *__restrict__ perms,
     piqmc_rand_state *rstate, const double *__restrict__ uniforms, uint64_t nuniforms,
     unsigned long long *consumed)
@@ -92,11 +103,20 @@ __global__ void __launch_bounds__(32) qa_det_kernel(
                     const int sidx = perm[t];
                     int8_t *row = s + (size_t)sidx * slices;
                     const int own = row[k];
-                    for (int n = 0; n < maxnb; n++) {
-                        const int j = idx[(size_t)sidx * maxnb + n];
-                        const float jv = J[(size_t)sidx * maxnb + n];
-                        const int other = (j == sidx) ? 1 : (int)s[(size_t)j * slices + k];
-                        ediff = __fadd_rn(ediff, signed_term(jv, own * other < 0));
+                    if (DENSE) {
+                        for (int si = 0; si < nspins; si++) {           // qmc.pyx:198-211
+                            const int other = (si == sidx) ? 1 : (int)s[(size_t)si * slices + k];
+                            const double jv = (sidx <= si) ? Jd[(size_t)sidx * nspins + si]
+                                                           : Jd[(size_t)si * nspins + sidx];
+                            ediff = dense_add(ediff, jv, own * other);
+                        }
+                    } else {
+                        for (int n = 0; n < maxnb; n++) {
+                            const int j = idx[(size_t)sidx * maxnb + n];
+                            const float jv = J[(size_t)sidx * maxnb + n];
+                            const int other = (j == sidx) ? 1 : (int)s[(size_t)j * slices + k];
+                            ediff = __fadd_rn(ediff, signed_term(jv, own * other < 0));
+                        }
                     }
                     ediff = __fadd_rn(ediff, signed_term(jperp, own * (int)row[tleft] < 0));
                     ediff = __fadd_rn(ediff, signed_term(jperp, own * (int)row[tright] < 0));
@@ -117,10 +137,12 @@ __global__ void __launch_bounds__(32) qa_det_kernel(
     if (consumed) consumed[r] = us.consumed;
 }
 
-// sa.Anneal, piqmc/sa.pyx:80-120.
+// sa.Anneal, piqmc/sa.pyx:80-120; DENSE: sa.Anneal_dense, piqmc/sa.pyx:126-187 (accepts on
+// ediff > 0, strictly, where the sparse variant accepts on >=).
+template <bool DENSE>
 __global__ void __launch_bounds__(32) sa_det_kernel(
     const float *__restrict__ temps, int nsched, int mcsteps, int nspins, int maxnb,
-    const int32_t *__restrict__ idx, const float *__restrict__ J, int nreplicas,
+    const int32_t *__restrict__ idx, const float *__restrict__ J, const double *__restrict__ Jd, int nreplicas,
     int8_t *__restrict__ spins, const int32_t *__restrict__ perms, piqmc_rand_state *rstate,
     const double *__restrict__ uniforms, uint64_t nuniforms, unsigned long long *consumed)
 {
@@ -142,14 +164,23 @@ __global__ void __launch_bounds__(32) sa_det_kernel(
                 const int sidx = perm[t];
                 const int own = s[sidx];
                 float ediff = 0.0f;                 // per spin (sa.pyx:119)
-                for (int n = 0; n < maxnb; n++) {
-                    const int j = idx[(size_t)sidx * maxnb + n];
-                    const float jv = J[(size_t)sidx * maxnb + n];
-                    const int other = (j == sidx) ? 1 : (int)s[j];
-                    ediff = __fadd_rn(ediff, signed_term(jv, own * other < 0));
+                if (DENSE) {
+                    for (int si = 0; si < nspins; si++) {               // sa.pyx:166-177
+                        const int other = (si == sidx) ? 1 : (int)s[si];
+                        const double jv = (sidx <= si) ? Jd[(size_t)sidx * nspins + si]
+                                                       : Jd[(size_t)si * nspins + sidx];
+                        ediff = dense_add(ediff, jv, own * other);
+                    }
+                } else {
+                    for (int n = 0; n < maxnb; n++) {
+                        const int j = idx[(size_t)sidx * maxnb + n];
+                        const float jv = J[(size_t)sidx * maxnb + n];
+                        const int other = (j == sidx) ? 1 : (int)s[j];
+                        ediff = __fadd_rn(ediff, signed_term(jv, own * other < 0));
+                    }
                 }
                 bool flip;
-                if (ediff >= 0.0f) {                // >= (sa.pyx:114)
+                if (DENSE ? (ediff > 0.0f) : (ediff >= 0.0f)) {   // >= (sa.pyx:114); dense: > (sa.pyx:180)
                     flip = true;
                 } else {
                     const double u = us.next();
@@ -216,12 +247,19 @@ __global__ void __launch_bounds__(64) sa_multispin_det_kernel(
 
 int launch_qa_det(piqmc_ctx *c, const float *d_jperp, int nsched, int mcsteps, int slices, float temp,
                   int nreplicas, int8_t *d_spins, const int32_t *d_perms, piqmc_rand_state *d_rstate,
-                  const double *d_uniforms, uint64_t nuniforms, unsigned long long *d_consumed)
+                  const double *d_uniforms, uint64_t nuniforms, unsigned long long *d_consumed,
+                  const double *d_dense, int dense_n)
 {
     dim3 block(32), grid((nreplicas + 31) / 32);
-    qa_det_kernel<<<grid, block, 0, c->stream>>>(d_jperp, nsched, mcsteps, slices, temp, c->nspins,
-                                                 c->maxnb, c->d_idx, c->d_J32, nreplicas, d_spins,
-                                                 d_perms, d_rstate, d_uniforms, nuniforms, d_consumed);
+    if (d_dense)
+        qa_det_kernel<true><<<grid, block, 0, c->stream>>>(d_jperp, nsched, mcsteps, slices, temp, dense_n, 0,
+                                                           nullptr, nullptr, d_dense, nreplicas, d_spins, d_perms,
+                                                           d_rstate, d_uniforms, nuniforms, d_consumed);
+    else
+        qa_det_kernel<false><<<grid, block, 0, c->stream>>>(d_jperp, nsched, mcsteps, slices, temp, c->nspins,
+                                                            c->maxnb, c->d_idx, c->d_J32, nullptr, nreplicas,
+                                                            d_spins, d_perms, d_rstate, d_uniforms, nuniforms,
+                                                            d_consumed);
     c->launches++;
     PIQMC_CUDA(cudaGetLastError());
     return PIQMC_OK;
@@ -229,12 +267,18 @@ int launch_qa_det(piqmc_ctx *c, const float *d_jperp, int nsched, int mcsteps, i
 
 int launch_sa_det(piqmc_ctx *c, const float *d_temps, int nsched, int mcsteps, int nreplicas,
                   int8_t *d_spins, const int32_t *d_perms, piqmc_rand_state *d_rstate,
-                  const double *d_uniforms, uint64_t nuniforms, unsigned long long *d_consumed)
+                  const double *d_uniforms, uint64_t nuniforms, unsigned long long *d_consumed,
+                  const double *d_dense, int dense_n)
 {
     dim3 block(32), grid((nreplicas + 31) / 32);
-    sa_det_kernel<<<grid, block, 0, c->stream>>>(d_temps, nsched, mcsteps, c->nspins, c->maxnb,
-                                                 c->d_idx, c->d_J32, nreplicas, d_spins, d_perms,
-                                                 d_rstate, d_uniforms, nuniforms, d_consumed);
+    if (d_dense)
+        sa_det_kernel<true><<<grid, block, 0, c->stream>>>(d_temps, nsched, mcsteps, dense_n, 0, nullptr, nullptr,
+                                                           d_dense, nreplicas, d_spins, d_perms, d_rstate,
+                                                           d_uniforms, nuniforms, d_consumed);
+    else
+        sa_det_kernel<false><<<grid, block, 0, c->stream>>>(d_temps, nsched, mcsteps, c->nspins, c->maxnb,
+                                                            c->d_idx, c->d_J32, nullptr, nreplicas, d_spins,
+                                                            d_perms, d_rstate, d_uniforms, nuniforms, d_consumed);
     c->launches++;
     PIQMC_CUDA(cudaGetLastError());
     return PIQMC_OK;

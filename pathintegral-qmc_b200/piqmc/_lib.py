@@ -51,6 +51,10 @@ SIGNATURES = {
                              c_void, c_u64, c_void]),
     "piqmc_sa_det": (c_int, [c_void, c_void, c_int, c_int, c_int, c_void, c_void, c_void, c_void,
                              c_u64, c_void]),
+    "piqmc_qa_dense_det": (c_int, [c_void, c_int, c_void, c_void, c_int, c_int, c_int, c_f, c_int, c_void,
+                                   c_void, c_void, c_void, c_u64, c_void]),
+    "piqmc_sa_dense_det": (c_int, [c_void, c_int, c_void, c_void, c_int, c_int, c_int, c_void, c_void,
+                                   c_void, c_void, c_u64, c_void]),
     "piqmc_sa_multispin_det": (c_int, [c_void, c_void, c_int, c_int, c_int, c_void, c_void, c_void]),
     "piqmc_jperp": (c_f, [c_d, c_int, c_f]),
     "piqmc_state_alloc": (c_int, [c_void, c_int, c_int]),

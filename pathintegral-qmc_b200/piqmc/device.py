@@ -143,6 +143,42 @@ class Device:
                                _ptr(uni), nuni, _ptr(consumed)))
         return consumed
 
+    @staticmethod
+    def _dense(J):
+        J = np.asarray(J)
+        if J.dtype != np.float64 or J.ndim != 2 or J.shape[0] != J.shape[1]:
+            raise ValueError("J must be a square float64 matrix")
+        return np.ascontiguousarray(J)
+
+    def qa_dense_det(self, sched, mcsteps, slices, temp, spins, J, perms, rstates=None, uniforms=None):
+        """qmc.QuantumAnneal_dense for R replicas, bit-exact.  J float64[N,N] (upper triangle +
+        diagonal read); spins int8[R,N,P] in place; other arguments as qa_det.  Needs no graph."""
+        sched = np.ascontiguousarray(sched, dtype=np.float64)
+        J = self._dense(J)
+        n, R = J.shape[0], spins.shape[0]
+        self._check_det(spins, (R, n, slices), perms, (R, sched.size * mcsteps, n), nspins=n)
+        consumed = np.zeros(R, dtype=np.uint64)
+        uni, nuni = self._uniforms(uniforms, R)
+        check(lib.piqmc_qa_dense_det(self._h, n, _ptr(J), _ptr(sched), sched.size, int(mcsteps), int(slices),
+                                     ctypes.c_float(temp), R, _ptr(spins), _ptr(perms),
+                                     None if rstates is None else ctypes.cast(rstates, ctypes.c_void_p),
+                                     _ptr(uni), nuni, _ptr(consumed)))
+        return consumed
+
+    def sa_dense_det(self, sched, mcsteps, spins, J, perms, rstates=None, uniforms=None):
+        """sa.Anneal_dense for R replicas, bit-exact.  spins int8[R,N] in place."""
+        sched = np.ascontiguousarray(sched, dtype=np.float64)
+        J = self._dense(J)
+        n, R = J.shape[0], spins.shape[0]
+        self._check_det(spins, (R, n), perms, (R, sched.size * mcsteps, n), nspins=n)
+        consumed = np.zeros(R, dtype=np.uint64)
+        uni, nuni = self._uniforms(uniforms, R)
+        check(lib.piqmc_sa_dense_det(self._h, n, _ptr(J), _ptr(sched), sched.size, int(mcsteps), R, _ptr(spins),
+                                     _ptr(perms),
+                                     None if rstates is None else ctypes.cast(rstates, ctypes.c_void_p),
+                                     _ptr(uni), nuni, _ptr(consumed)))
+        return consumed
+
     def sa_multispin_det(self, sched, mcsteps, words, perms, rands):
         """sa.Anneal_multispin for G groups of 64 replicas.  words uint64[G,N] in place,
         perms int32[G,nsweeps,N], rands float64[G,nsweeps*N,64]."""
@@ -159,14 +195,16 @@ class Device:
         check(lib.piqmc_sa_multispin_det(self._h, _ptr(sched), sched.size, int(mcsteps), G, _ptr(words),
                                          _ptr(perms), _ptr(rands)))
 
-    def _check_det(self, spins, sshape, perms, pshape):
-        if self.nspins == 0:
+    def _check_det(self, spins, sshape, perms, pshape, nspins=None):
+        if nspins is None:
+            nspins = self.nspins
+        if nspins == 0:
             raise ValueError("set_graph has not been called")
         if spins.dtype != np.int8 or not spins.flags.c_contiguous or spins.shape != sshape:
             raise ValueError("spins must be C-contiguous int8 of shape %s" % (sshape,))
         if perms.dtype != np.int32 or not perms.flags.c_contiguous or perms.shape != pshape:
             raise ValueError("perms must be C-contiguous int32 of shape %s" % (pshape,))
-        if perms.size and (perms.min() < 0 or perms.max() >= self.nspins):
+        if perms.size and (perms.min() < 0 or perms.max() >= nspins):
             raise ValueError("perms entries out of range")
 
     @staticmethod

@@ -64,6 +64,29 @@ def QuantumAnneal(sched, mcsteps, slices, temp, nspins, confs, nbs, rng, device=
     return None
 
 
+def QuantumAnneal_dense(sched, mcsteps, slices, temp, nspins, confs, J, rng, device=None):
+    """qmc.QuantumAnneal with a dense coupling matrix @J (float64[nspins, nspins]; off-diagonals are
+    couplings, of which only the upper triangle is read, the diagonal holds the local fields).
+    Bit-exact replay of the reference (piqmc/qmc.pyx:141-242), same as-shipped behaviour as
+    QuantumAnneal (per-slice reset of the float32 energy difference, Trotter neighbours `slices-1`
+    and `1`, lazy libc rand()); the couplings stay float64.  @confs is updated in place.  Returns None."""
+    sched = _f64(sched, 1, "sched")
+    J = _f64(J, 2, "J")
+    nspins, slices, mcsteps = int(nspins), int(slices), int(mcsteps)
+    confs = _check_confs(confs, nspins, slices)
+    if J.shape != (nspins, nspins):
+        raise ValueError("J must have shape (nspins, nspins) = (%d, %d), got %s" % (nspins, nspins, J.shape))
+    d = device or _dev.default_device()
+    perms = _draw_perms(rng, nspins, sched.size * mcsteps)[None]
+    spins = np.ascontiguousarray(_spins_i8(confs, "confs"))[None].copy()
+    st = (RandState * 1)()
+    st[0] = _dev.capture_libc_rand()
+    d.qa_dense_det(sched, mcsteps, slices, temp, spins, J, np.ascontiguousarray(perms), rstates=st)
+    _dev.restore_libc_rand(st[0])
+    confs[:, :] = spins[0]
+    return None
+
+
 def QuantumAnnealBatch(sched, mcsteps, slices, temp, nspins, confs, nbs, rngs, srand_seeds, device=None):
     """R independent QuantumAnneal runs in one launch (deterministic, bit-exact per replica).
     confs: [R, nspins, slices] (+-1, float64 or int8); rngs: one RandomState per replica;

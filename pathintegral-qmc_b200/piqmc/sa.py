@@ -19,7 +19,7 @@ from . import device as _dev
 from . import tools as _tools
 from ._lib import RandState, lib
 
-__all__ = ["ClassicalIsingEnergy", "Anneal", "Anneal_parallel", "Anneal_multispin", "AnnealBatch",
+__all__ = ["ClassicalIsingEnergy", "Anneal", "Anneal_dense", "Anneal_parallel", "Anneal_multispin", "AnnealBatch",
            "AnnealReplicas"]
 
 
@@ -82,6 +82,28 @@ def Anneal(sched, mcsteps, svec, nbs, rng, device=None):
     st = (RandState * 1)()
     st[0] = _dev.capture_libc_rand()
     d.sa_det(sched, int(mcsteps), spins, np.ascontiguousarray(perms), rstates=st)
+    _dev.restore_libc_rand(st[0])
+    svec[:] = spins[0]
+    return None
+
+
+def Anneal_dense(sched, mcsteps, svec, J, rng, device=None):
+    """sa.Anneal with a dense coupling matrix @J (float64[N, N]; upper triangle + diagonal = local
+    fields).  Bit-exact replay of the reference (piqmc/sa.pyx:126-187); note that this variant
+    accepts on ediff > 0 where sa.Anneal accepts on ediff >= 0, and keeps the couplings in
+    float64.  @svec is updated in place.  Returns None."""
+    sched = _f64(sched, 1, "sched")
+    svec = _f64(svec, 1, "svec")
+    J = _f64(J, 2, "J")
+    n = svec.size
+    if J.shape != (n, n):
+        raise ValueError("J must have shape (%d, %d), got %s" % (n, n, J.shape))
+    d = device or _dev.default_device()
+    perms = _draw_perms(rng, n, sched.size * int(mcsteps))[None]
+    spins = _spins_i8(svec, "svec")[None].copy()
+    st = (RandState * 1)()
+    st[0] = _dev.capture_libc_rand()
+    d.sa_dense_det(sched, int(mcsteps), spins, J, np.ascontiguousarray(perms), rstates=st)
     _dev.restore_libc_rand(st[0])
     svec[:] = spins[0]
     return None

@@ -52,6 +52,78 @@ def test_anneal_dropin_golden(golden, dev, name):
     np.testing.assert_allclose(e, vec[name + "__energy"][0], rtol=1e-12, atol=1e-12)
 
 
+def _dense_cases(kind):
+    import json
+    import os
+    vec = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_dense.npz"))
+    return vec, [c for c in json.loads(str(vec["cases_json"])) if c["kind"] == kind]
+
+
+@pytest.mark.parametrize("k", range(7))
+def test_quantumanneal_dense_dropin_golden(dev, k):
+    """piqmc.qmc.QuantumAnneal_dense called like the reference's (qmc.pyx:141-242; F-strided confs
+    view, shared rng, process-global libc stream) reproduces the reference's output and leaves
+    both random streams where the reference leaves them."""
+    import piqmc.qmc as qmc
+    vec, cs = _dense_cases("qa_dense")
+    case = cs[k]
+    J = vec["J_" + case["inst"]]
+    n, P = J.shape[0], case["P"]
+    rng = np.random.RandomState(case["rng_seed"])
+    init = np.array([2 * rng.randint(2) - 1 for _ in range(n)], dtype=np.float64)
+    confs = np.tile(init, (P, 1)).T
+    sched = np.linspace(case["sched"][0], case["sched"][1], int(case["sched"][2]))
+    libc = ctypes.CDLL(None)
+    libc.srand(case["srand_seed"])
+    assert qmc.QuantumAnneal_dense(sched, case["mcsteps"], P, case["T"], n, confs, J, rng) is None
+    assert np.array_equal(confs.astype(np.int8), vec[case["name"] + "__final"])
+    assert [libc.rand() for _ in range(4)] == list(vec[case["name"] + "__libc_next"])
+    assert list(rng.randint(1 << 30, size=4)) == list(vec[case["name"] + "__rng_next"])
+
+
+@pytest.mark.parametrize("k", range(5))
+def test_anneal_dense_dropin_golden(dev, k):
+    """piqmc.sa.Anneal_dense == the reference's sa.Anneal_dense (sa.pyx:126-187)."""
+    import piqmc.sa as sa
+    vec, cs = _dense_cases("sa_dense")
+    case = cs[k]
+    J = vec["J_" + case["inst"]]
+    n = J.shape[0]
+    rng = np.random.RandomState(case["rng_seed"])
+    sv = np.array([2 * rng.randint(2) - 1 for _ in range(n)], dtype=np.float64)
+    sched = np.linspace(case["sched"][0], case["sched"][1], int(case["sched"][2]))
+    libc = ctypes.CDLL(None)
+    libc.srand(case["srand_seed"])
+    assert sa.Anneal_dense(sched, case["mcsteps"], sv, J, rng) is None
+    assert np.array_equal(sv.astype(np.int8), vec[case["name"] + "__final"])
+    assert [libc.rand() for _ in range(4)] == list(vec[case["name"] + "__libc_next"])
+    assert list(rng.randint(1 << 30, size=4)) == list(vec[case["name"] + "__rng_next"])
+
+
+def test_dense_equals_sparse_on_float32_couplings(golden, dev):
+    """With couplings exactly representable in float32 the dense and the sparse QA replays agree
+    (they differ only in where the coupling is narrowed), replica by replica in one launch."""
+    vec = golden["vec"]
+    nbs = vec["nbs_boixo16"]
+    n, P, R = 16, 6, 5
+    J = np.zeros((n, n))
+    for i in range(n):
+        for j, v in nbs[i]:
+            j = int(j)
+            if v != 0.0:
+                J[min(i, j), max(i, j)] = np.float32(v)
+    sched = np.linspace(1.0, 1e-8, 7)
+    rng0 = np.random.RandomState(3)
+    spins = (2 * rng0.randint(2, size=(R, n, 1)) - 1).astype(np.int8).repeat(P, axis=2)
+    perms = np.stack([O.make_perms(np.random.RandomState(r), n, sched.size * 2) for r in range(R)])
+    from piqmc import device
+    a, b = spins.copy(), spins.copy()
+    dev.set_graph(nbs)
+    ca = dev.qa_det(sched, 2, P, 0.05, a, perms, rstates=device.rand_states(range(R)))
+    cb = dev.qa_dense_det(sched, 2, P, 0.05, b, J, perms, rstates=device.rand_states(range(R)))
+    assert np.array_equal(a, b) and np.array_equal(ca, cb)
+
+
 def test_qa_batch_matches_oracle_per_replica(golden, dev):
     """R replicas in one launch (replica r: RandomState(r), srand(r)) == R oracle runs."""
     import piqmc.qmc as qmc

@@ -5,6 +5,7 @@ The goldens in tests/golden/ were produced by the reference's own compiled Cytho
 the reference's own test-suite (testing/test_core.py, testing/test_boixo.py) on the oracle.
 """
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -95,6 +96,51 @@ def test_sa_reference_golden(golden, name):
     assert consumed == int(vec[name + "__consumed"])
     assert O.lib().oracle_glibc_rand(ctypes.byref(g)) == int(vec[name + "__libc_next"])
     assert rng.randint(1 << 30) == int(vec[name + "__rng_next"])
+
+
+def _dense_cases(kind):
+    import json
+    vec = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_dense.npz"))
+    return vec, [c for c in json.loads(str(vec["cases_json"])) if c["kind"] == kind]
+
+
+@pytest.mark.parametrize("k", range(7))
+def test_qa_dense_golden(k):
+    """oracle_qa_dense == the reference's qmc.QuantumAnneal_dense (qmc.pyx:141-242): spins and the
+    positions both random streams are left at."""
+    vec, cs = _dense_cases("qa_dense")
+    case = cs[k]
+    J = vec["J_" + case["inst"]]
+    n, P = J.shape[0], case["P"]
+    rng = np.random.RandomState(case["rng_seed"])
+    init = np.array([2 * rng.randint(2) - 1 for _ in range(n)], dtype=np.float64)
+    assert np.array_equal(init.astype(np.int8), vec[case["name"] + "__init"])
+    confs = np.tile(init, (P, 1)).T
+    sched = np.linspace(case["sched"][0], case["sched"][1], int(case["sched"][2]))
+    perms = O.make_perms(rng, n, sched.size * case["mcsteps"])
+    g = O.glibc_state(case["srand_seed"])
+    O.qa_dense(sched, case["mcsteps"], P, case["T"], n, confs, J, perms, gstate=g)
+    assert np.array_equal(confs.astype(np.int8), vec[case["name"] + "__final"])
+    assert [O.lib().oracle_glibc_rand(ctypes.byref(g)) for _ in range(4)] == list(vec[case["name"] + "__libc_next"])
+    assert list(rng.randint(1 << 30, size=4)) == list(vec[case["name"] + "__rng_next"])
+
+
+@pytest.mark.parametrize("k", range(5))
+def test_sa_dense_golden(k):
+    """oracle_sa_dense == the reference's sa.Anneal_dense (sa.pyx:126-187)."""
+    vec, cs = _dense_cases("sa_dense")
+    case = cs[k]
+    J = vec["J_" + case["inst"]]
+    n = J.shape[0]
+    rng = np.random.RandomState(case["rng_seed"])
+    sv = np.array([2 * rng.randint(2) - 1 for _ in range(n)], dtype=np.float64)
+    sched = np.linspace(case["sched"][0], case["sched"][1], int(case["sched"][2]))
+    perms = O.make_perms(rng, n, sched.size * case["mcsteps"])
+    g = O.glibc_state(case["srand_seed"])
+    O.sa_dense(sched, case["mcsteps"], sv, J, perms, gstate=g)
+    assert np.array_equal(sv.astype(np.int8), vec[case["name"] + "__final"])
+    assert [O.lib().oracle_glibc_rand(ctypes.byref(g)) for _ in range(4)] == list(vec[case["name"] + "__libc_next"])
+    assert list(rng.randint(1 << 30, size=4)) == list(vec[case["name"] + "__rng_next"])
 
 
 def test_parallel1_variants_golden(golden):

@@ -1,18 +1,9 @@
 run() { echo "$@"; env "$@" timeout 120 python bench.py --no-cpu --steps 50 $EXTRA 2>&1 | grep -o '"value": [0-9.e+]*' | head -1; }
 EXTRA=""
-run PIQMC_MINB=7
-run PIQMC_MINB=8
-run PIQMC_MINB=8 PIQMC_ROWS_PER_BLOCK=256
-run PIQMC_MINB=7 PIQMC_ROWS_PER_BLOCK=256
-run PIQMC_MINB=7 PIQMC_ROWS_PER_BLOCK=1024
+run PIQMC_BLOCKS=592
+run PIQMC_BLOCKS=888
+run PIQMC_BLOCKS=1036
 EXTRA="--replicas 512"
-run PIQMC_MINB=7
-run PIQMC_MINB=8
-EXTRA="--replicas 1024"
-run PIQMC_MINB=7
-run PIQMC_MINB=8
-run PIQMC_MINB=8 PIQMC_ROWS_PER_BLOCK=128
-EXTRA="--replicas 2048"
-run PIQMC_MINB=7
-run PIQMC_MINB=8
-run PIQMC_MINB=7 PIQMC_ROWS_PER_BLOCK=256
+run PIQMC_BLOCKS=444
+run PIQMC_BLOCKS=592
+run PIQMC_BLOCKS=888
