@@ -95,6 +95,64 @@ def Generate2DIsingInstance(nRows, rng):
     return J
 
 
+def Generate2DLattice(nrows, ncols, rng, periodic=0):
+    """nrows x ncols square-lattice Ising model, couplings uniform in [-1e-8, 1e-8], upper-
+    triangular DOK; @periodic=1 closes both directions into a torus.
+
+    Reference: piqmc/tools.pyx:132-176.  One draw per stored bond in the reference's order (for
+    every spin: wrap-around vertical, wrap-around horizontal, right neighbour, bottom neighbour),
+    so the same @rng gives the same matrix; O(N) instead of the reference's O(N^2) column scan."""
+    nrows, ncols = int(nrows), int(ncols)
+    nspins = nrows * ncols
+    J = sps.dok_matrix((nspins, nspins), dtype=np.float64)
+    for jrow in range(nspins):
+        if jrow < ncols and periodic:
+            J[jrow, jrow + ncols * (nrows - 1)] = rng.uniform(low=-1e-8, high=1e-8)
+        if jrow % ncols == 0 and periodic:
+            J[jrow, jrow + ncols - 1] = rng.uniform(low=-1e-8, high=1e-8)
+        # the reference scans columns upwards: right neighbour (jrow+1) before bottom (jrow+ncols)
+        if jrow + 1 < nspins and jrow % ncols != ncols - 1:
+            J[jrow, jrow + 1] = rng.uniform(low=-1e-8, high=1e-8)
+        if jrow + ncols < nspins:
+            J[jrow, jrow + ncols] = rng.uniform(low=-1e-8, high=1e-8)
+    return J
+
+
+def GenerateKblockLattice(nrows, ncols, rng, k=1):
+    """Lattice in which every spin is coupled to the spins on the square rings of radius 1..@k
+    around it (open boundaries), couplings uniform in [-1e-8, 1e-8], upper-triangular DOK.
+
+    Reference: piqmc/tools.pyx:178-272.  Follows the reference ring by ring and side by side (top,
+    bottom, left, right), including how it clips a ring at the lattice border and that a ring
+    corner shared by two sides is drawn twice (the later draw wins), so the same @rng gives the
+    same matrix."""
+    nrows, ncols, k = int(nrows), int(ncols), int(k)
+    nspins = nrows * ncols
+    J = sps.dok_matrix((nspins, nspins), dtype=np.float64)
+    for ispin in range(nspins):
+        col = ispin % ncols
+        room_right = ncols - 1 - col                       # spins to the right in this lattice row
+        for ki in range(1, k + 1):
+            kleft = min(ki, col)
+            kright = min(ki, room_right)
+            kup = ki
+            while ispin - kup * ncols < 0:
+                kup -= 1
+            kdown = ki
+            while ispin + kdown * ncols >= nspins:
+                kdown -= 1
+            corner = max(ispin - kup * ncols - kleft, 0)   # top-left spin of the (clipped) ring
+            width, height = kleft + kright, kup + kdown
+            ring = [corner + r for r in range(width + 1)]                              # top side
+            ring += [corner + r + height * ncols for r in range(width + 1)]            # bottom side
+            ring += [corner + r * ncols for r in range(1, height + 1)]                 # left side
+            ring += [corner + width + r * ncols for r in range(1, height + 1)]         # right side
+            for idx in ring:
+                if ispin < idx:
+                    J[ispin, idx] = rng.uniform(low=-1e-8, high=1e-8)
+    return J
+
+
 # ---------------------------------------------------------------------------------------------
 # Additions for the B200 kernels (no counterpart in the reference)
 # ---------------------------------------------------------------------------------------------

@@ -124,3 +124,21 @@ def test_pack_unpack_words():
     assert w.shape == (3, 17) and w.dtype == np.uint64
     assert np.array_equal(tools.UnpackWords(w, 20), s)
     assert (int(w[1, 5]) >> 7) & 1 == (1 if s[1, 7, 5] < 0 else 0)
+
+
+def test_lattice_generators_match_reference():
+    """tools.Generate2DLattice / GenerateKblockLattice (tools.pyx:132-272): same matrix, same key
+    order and same number of draws as the reference's own functions (tests/golden/ref_lattices.npz)."""
+    import json
+    import os
+    vec = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_lattices.npz"))
+    for k, c in enumerate(json.loads(str(vec["cases_json"]))):
+        rng = np.random.RandomState(c["seed"])
+        if c["kind"] == "lattice":
+            J = tools.Generate2DLattice(c["nrows"], c["ncols"], rng, c["arg"])
+        else:
+            J = tools.GenerateKblockLattice(c["nrows"], c["ncols"], rng, c["arg"])
+        assert np.array_equal(J.toarray(), vec["J%d" % k]), c
+        assert np.array_equal(np.array(list(J.keys()), dtype=np.int64).reshape(-1, 2), vec["keys%d" % k]), c
+        assert rng.randint(1 << 30) == int(vec["next%d" % k][0]), c
+        assert (J - sps.triu(J)).nnz == 0
