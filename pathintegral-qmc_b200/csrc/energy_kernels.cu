@@ -5,67 +5,60 @@
 // Packed path: the ELL table of tools.GenerateNeighbors lists every stored key (a, b) in both
 // endpoint rows (tools.pyx:84-92), so each key is counted once by keeping only the entries whose
 // neighbour index is larger than the row index; diagonal keys appear once as self-neighbours.
-// Summation order is fixed (no atomics): results are reproducible.
+// Summation order is fixed (no atomics): results are reproducible.  Padding entries (0, 0.0) of a
+// row i > 0 point at spin 0 < i and are skipped; those of row 0 add +-0.
 #include "common.cuh"
 
 namespace {
 
-constexpr int EN_CHUNKS = 4;   // threadIdx.y sub-chunks per block
+constexpr int EN_ROWS = 32;     // rows per block: 8 warps x 4 rows
+constexpr int EN_THREADS = 256;
 
-// grid = (nblocks_x, nrows); block = (64 lanes, EN_CHUNKS).  Thread (lane, y) of block bx sums
-// spins i = (bx*EN_CHUNKS + y), stepping by gridDim.x*EN_CHUNKS.  All 64 lanes of a warp pair
-// read the same words (broadcast), each extracting its own bit.
-__global__ void __launch_bounds__(64 * EN_CHUNKS) energy_partial_kernel(
+// Thread = (row, group of 8 lanes): a warp covers 4 consecutive rows x 8 lane groups, so every
+// word load of a warp is one 32-byte sector (4 rows x 8 bytes, each broadcast to the 8 threads of
+// its row) and the table entries (idx, J) are warp-uniform.  grid = (row tiles, spin splits);
+// block (tile, sp) sums spins sp, sp + nsplit, ... for its 32 rows; 8 float64 accumulators per
+// thread, one per lane.  Fields and bonds go into the same sum: E = -(sum).
+__global__ void __launch_bounds__(EN_THREADS) energy_partial_kernel(
     const uint64_t *__restrict__ words, int nspins, int nrows, int maxnb,
-    const int32_t *__restrict__ idx, const double *__restrict__ J, int lanes, double *__restrict__ part)
+    const int32_t *__restrict__ idx, const double *__restrict__ J, double *__restrict__ part)
 {
-    const int lane = threadIdx.x, y = threadIdx.y, row = blockIdx.y;
-    const uint64_t *wrow = words + row;               // word of spin s at wrow[s*nrows]
-    double eq = 0.0, el = 0.0;
-    for (int i = blockIdx.x * EN_CHUNKS + y; i < nspins; i += gridDim.x * EN_CHUNKS) {
+    const int lg = threadIdx.x & 7;
+    const int row = blockIdx.x * EN_ROWS + (threadIdx.x >> 3);
+    const bool live = row < nrows;
+    const uint64_t *wrow = words + (live ? row : 0);   // word of spin s at wrow[s*nrows]
+    double acc[8];
+#pragma unroll
+    for (int b = 0; b < 8; b++) acc[b] = 0.0;
+    for (int i = blockIdx.y; i < nspins; i += gridDim.y) {
         const uint64_t w = wrow[(size_t)i * nrows];
         for (int n = 0; n < maxnb; n++) {
             const int j = idx[(size_t)i * maxnb + n];
             if (j < i) continue;                              // the key is counted in row j
-            const double jv = J[(size_t)i * maxnb + n];
-            if (j == i) {
-                el += ((w >> lane) & 1) ? -jv : jv;
-            } else {
-                const uint64_t x = w ^ wrow[(size_t)j * nrows];
-                eq += ((x >> lane) & 1) ? -jv : jv;
-            }
+            const long long jb = __double_as_longlong(J[(size_t)i * maxnb + n]);
+            const uint64_t x = (j == i) ? w : (w ^ wrow[(size_t)j * nrows]);
+            const uint32_t bits = (uint32_t)(x >> (8 * lg)) & 0xFFu;
+#pragma unroll
+            for (int b = 0; b < 8; b++)      // +J where the lane agrees (s_i s_j = +1), -J where it does not
+                acc[b] += __longlong_as_double(jb ^ ((long long)((bits >> b) & 1u) << 63));
         }
     }
-    __shared__ double sq[EN_CHUNKS][64], sl[EN_CHUNKS][64];
-    sq[y][lane] = eq;
-    sl[y][lane] = el;
-    __syncthreads();
-    if (y == 0 && lane < lanes) {
-        double q = 0.0, l = 0.0;
-        for (int c = 0; c < EN_CHUNKS; c++) {
-            q += sq[c][lane];
-            l += sl[c][lane];
-        }
-        // part[(row*gridDim.x + bx)*2*64 + {0,1}*64 + lane]
-        double *p = part + ((size_t)row * gridDim.x + blockIdx.x) * 128;
-        p[lane] = q;
-        p[64 + lane] = l;
+    if (live) {
+        double *p = part + ((size_t)blockIdx.y * nrows + row) * 64 + 8 * lg;
+#pragma unroll
+        for (int b = 0; b < 8; b++) p[b] = acc[b];
     }
 }
 
-__global__ void energy_final_kernel(const double *__restrict__ part, int nblocks, int nrows, int lanes,
+__global__ void energy_final_kernel(const double *__restrict__ part, int nsplit, int nrows, int lanes,
                                     double *__restrict__ out)
 {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= nrows * lanes) return;
     const int row = tid / lanes, lane = tid % lanes;
-    double q = 0.0, l = 0.0;
-    for (int b = 0; b < nblocks; b++) {
-        const double *p = part + ((size_t)row * nblocks + b) * 128;
-        q += p[lane];
-        l += p[64 + lane];
-    }
-    out[tid] = -q - l;
+    double q = 0.0;
+    for (int b = 0; b < nsplit; b++) q += part[((size_t)b * nrows + row) * 64 + lane];   // fixed order
+    out[tid] = -q;
 }
 
 // COO path for host configurations (drop-in ClassicalIsingEnergy): one block per configuration.
@@ -94,23 +87,24 @@ __global__ void __launch_bounds__(256) energy_coo_kernel(
 
 int launch_energy(piqmc_ctx *c)
 {
-    int nbx = (c->nspins + EN_CHUNKS * 64 - 1) / (EN_CHUNKS * 64);   // >= 64 spins per thread-column
-    if (nbx < 1) nbx = 1;
-    if (nbx > 64) nbx = 64;
-    const size_t need = (size_t)c->nrows * nbx * 128;
+    const int tiles = (c->nrows + EN_ROWS - 1) / EN_ROWS;
+    // enough blocks for every SM several times over, but at least ~64 spins per block
+    int nsplit = (8 * std::max(c->sm_count, 1) + tiles - 1) / tiles;
+    nsplit = std::max(1, std::min(nsplit, std::min(64, (c->nspins + 63) / 64)));
+    const size_t need = (size_t)nsplit * c->nrows * 64;
     if (need > c->epart_elems) {
         if (c->d_epart) PIQMC_CUDA(cudaFree(c->d_epart));
         c->d_epart = nullptr;
         PIQMC_CUDA(cudaMalloc(&c->d_epart, need * sizeof(double)));
         c->epart_elems = need;
     }
-    dim3 block(64, EN_CHUNKS), grid(nbx, c->nrows);
-    energy_partial_kernel<<<grid, block, 0, c->stream>>>(c->d_words, c->nspins, c->nrows, c->maxnb,
-                                                        c->d_idx, c->d_J64, c->lanes, c->d_epart);
+    dim3 grid(tiles, nsplit);
+    energy_partial_kernel<<<grid, EN_THREADS, 0, c->stream>>>(c->d_words, c->nspins, c->nrows, c->maxnb, c->d_idx,
+                                                             c->d_J64, c->d_epart);
     c->launches++;
     PIQMC_CUDA(cudaGetLastError());
     const int n = c->nrows * c->lanes;
-    energy_final_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_epart, nbx, c->nrows, c->lanes,
+    energy_final_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_epart, nsplit, c->nrows, c->lanes,
                                                                c->d_energy);
     c->launches++;
     PIQMC_CUDA(cudaGetLastError());

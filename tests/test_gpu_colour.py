@@ -330,7 +330,9 @@ def test_config4_state_populations_vs_reference(golden, dev, inst):
     table = np.array([np.append(a[big], a[~big].sum()), np.append(b[big], b[~big].sum())])
     table = table[:, table.sum(axis=0) > 0]
     p_chi = chi2_contingency(table)[1]
-    p_ks = ks_2samp_p(out["energies"], ref_en)
+    # 8-spin instances have a handful of discrete energy levels: compare them as levels (the device
+    # reduction and the reference's dense matvec sum in different orders and differ in the last ulp)
+    p_ks = ks_2samp_p(np.round(out["energies"], 9), np.round(ref_en, 9))
     print(inst, "states used", int(big.sum()), "chi2 p %.3f  KS(energy) p %.3f  mean E mine %.3f ref %.3f"
           % (p_chi, p_ks, out["energies"].mean(), ref_en.mean()))
     assert p_chi > 0.01 and p_ks > 0.01
