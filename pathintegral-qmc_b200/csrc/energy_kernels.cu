@@ -88,9 +88,9 @@ __global__ void __launch_bounds__(256) energy_coo_kernel(
 int launch_energy(piqmc_ctx *c)
 {
     const int tiles = (c->nrows + EN_ROWS - 1) / EN_ROWS;
-    // enough blocks for every SM several times over, but at least ~64 spins per block
-    int nsplit = (8 * std::max(c->sm_count, 1) + tiles - 1) / tiles;
-    nsplit = std::max(1, std::min(nsplit, std::min(64, (c->nspins + 63) / 64)));
+    // the split of the spin sum depends on the graph only, never on the number of rows: a replica's
+    // energy is the same float64 whichever shard of the replicas it is computed in
+    const int nsplit = std::max(1, std::min(64, (c->nspins + 63) / 64));
     const size_t need = (size_t)nsplit * c->nrows * 64;
     if (need > c->epart_elems) {
         if (c->d_epart) PIQMC_CUDA(cudaFree(c->d_epart));

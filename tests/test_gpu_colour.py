@@ -442,3 +442,50 @@ def test_world_line_moves_bit_exact(golden, dev, inst, P, T, trotter):
     assert np.array_equal(want, got)
     if T > 0.1:
         assert not np.array_equal(want, plain)          # at these temperatures some global moves are accepted
+
+
+# --------------------------------------------------------------------- BASELINE.json full size
+def test_config5_full_size_properties(dev):
+    """BASELINE configs[4] at full size (256x256 Gaussian torus, P = 64, R = 4096; the oracle would
+    need hours), through properties that do not depend on size:
+      * reproducibility: the same seed gives the same 2.1 GB state, word for word;
+      * sharding invariance: replicas [0, R) in one state == [0, R/2) and [R/2, R) run on their own
+        with the global replica id in the Philox key (what the multi-GPU path relies on);
+      * energy consistency: device energies == ClassicalIsingEnergy recomputed on the host from the
+        downloaded words, for sampled (replica, slice) pairs, to 1e-12 relative;
+      * every energy lies above the trivial bound -sum|J| and the anneal lowers the mean energy."""
+    import piqmc.qmc as qmc
+    import piqmc.tools as T
+    L, P, R, steps = 256, 64, 4096, 6
+    n = L * L
+    nbs, _ = T.GaussianTorusNeighbors(L, 2024)
+    color = T.TorusNaturalLevels(L)
+    sched = np.linspace(1.5, 1e-8, steps)
+    full = qmc.QuantumAnnealReplicas(sched, 1, P, 0.01, n, None, nbs, 2024, color=color, nreplicas=R, device=dev)
+    w_full = full["words"].copy()
+    e_full = full["energies"].copy()
+    again = qmc.QuantumAnnealReplicas(sched, 1, P, 0.01, n, None, nbs, 2024, color=color, nreplicas=R, device=dev)
+    assert np.array_equal(again["words"], w_full) and np.array_equal(again["energies"], e_full)
+    del again
+    half = R // 2
+    for r0 in (0, half):
+        part = qmc.QuantumAnnealReplicas(sched, 1, P, 0.01, n, None, nbs, 2024, color=color, nreplicas=half,
+                                         replica0=r0, device=dev)
+        assert np.array_equal(part["words"], w_full[r0:r0 + half])
+        assert np.array_equal(part["energies"], e_full[r0:r0 + half])
+        del part
+    # host recomputation of the energy: bonds (i, right), (i, down), each once
+    idx = nbs[:, :, 0].astype(np.int64)
+    Jv = nbs[:, :, 1]
+    ii = np.repeat(np.arange(n), 4).reshape(n, 4)
+    once = idx > ii
+    bi, bj, bJ = ii[once], idx[once], Jv[once]
+    rng = np.random.RandomState(0)
+    for r, k in zip(rng.randint(R, size=6), rng.randint(P, size=6)):
+        s = 1.0 - 2.0 * ((w_full[r] >> np.uint64(k)) & np.uint64(1)).astype(np.float64)
+        ref = -np.sum(bJ * s[bi] * s[bj])
+        np.testing.assert_allclose(e_full[r, k], ref, rtol=1e-12)
+    assert e_full.min() > -np.abs(bJ).sum()
+    start = qmc.QuantumAnnealReplicas(sched[:0], 1, P, 0.01, n, None, nbs, 2024, color=color, nreplicas=64,
+                                      device=dev)
+    assert e_full.mean() < start["energies"].mean() - 0.5 * n
