@@ -1,9 +1,7 @@
 run() { echo "$@"; env "$@" timeout 120 python bench.py --no-cpu --steps 50 $EXTRA 2>&1 | grep -o '"value": [0-9.e+]*' | head -1; }
+timeout 300 python -m pytest tests/test_gpu_colour.py -m gpu -x -q -k "bit_exact or world or periodic" 2>&1 | tail -2
 EXTRA=""
-run PIQMC_BLOCKS=592
-run PIQMC_BLOCKS=888
-run PIQMC_BLOCKS=1036
+run PIQMC_MINB=9
+run PIQMC_MINB=8
 EXTRA="--replicas 512"
-run PIQMC_BLOCKS=444
-run PIQMC_BLOCKS=592
-run PIQMC_BLOCKS=888
+run PIQMC_MINB=9
