@@ -130,12 +130,14 @@ static void build_unit_recs(const piqmc_ctx *h, const int32_t *level, const int3
         float J[4];
         uint8_t dep[4];
         for (int n = 0; n < 4; n++) {
-            nb[n] = i;
+            // self entries (local fields) and unused columns read the all-zero row behind the last
+            // spin (piqmc_state_alloc), so the kernel loads every column unconditionally
+            nb[n] = h->nspins;
             J[n] = 0.0f;
             dep[n] = 0;
             if (n < mb) {
                 const size_t e = (size_t)i * h->maxnb + n;
-                nb[n] = h->h_idx[e];
+                if (h->h_idx[e] != i) nb[n] = h->h_idx[e];
                 J[n] = h->h_J32[e];
                 if (h->h_live[e]) dep[n] = level[h->h_idx[e]] < level[i] ? 2 : 1;
             }
@@ -757,9 +759,10 @@ int piqmc_state_alloc(piqmc_handle h, int nrows, int lanes)
     }
     PIQMC_CUDA(cudaStreamSynchronize(h->stream));
     free_state(h);
-    PIQMC_CUDA(cudaMalloc(&h->d_words, (size_t)nrows * h->nspins * sizeof(uint64_t)));
+    // one extra, all-zero row behind the last spin: the "neighbour" of self entries and unused columns
+    PIQMC_CUDA(cudaMalloc(&h->d_words, (size_t)nrows * (h->nspins + 1) * sizeof(uint64_t)));
     PIQMC_CUDA(cudaMalloc(&h->d_energy, (size_t)nrows * lanes * sizeof(double)));
-    PIQMC_CUDA(cudaMemsetAsync(h->d_words, 0, (size_t)nrows * h->nspins * sizeof(uint64_t), h->stream));
+    PIQMC_CUDA(cudaMemsetAsync(h->d_words, 0, (size_t)nrows * (h->nspins + 1) * sizeof(uint64_t), h->stream));
     h->nrows = nrows;
     h->lanes = lanes;
     return PIQMC_OK;
@@ -775,7 +778,8 @@ int piqmc_state_replicas_to_slices(piqmc_handle h, int nreplicas, int slices)
     uint64_t *src = h->d_words;
     const int src_rows = h->nrows;
     uint64_t *dst = nullptr;
-    PIQMC_CUDA(cudaMalloc(&dst, (size_t)nreplicas * h->nspins * sizeof(uint64_t)));
+    PIQMC_CUDA(cudaMalloc(&dst, (size_t)nreplicas * (h->nspins + 1) * sizeof(uint64_t)));   // + the zero row
+    cudaMemsetAsync(dst + (size_t)nreplicas * h->nspins, 0, (size_t)nreplicas * sizeof(uint64_t), h->stream);
     int rc = launch_replicas_to_slices(h, src, src_rows, dst, nreplicas, slices);
     cudaError_t e = cudaStreamSynchronize(h->stream);
     if (rc != PIQMC_OK || e != cudaSuccess) {

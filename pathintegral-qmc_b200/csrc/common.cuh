@@ -35,8 +35,8 @@ void piqmc_set_error(const char *fmt, ...);
 struct alignas(16) PiqmcUnitRec {
     int32_t spin;
     int32_t sweepoff;     // sweep lag of this member in the period-major order (0 for per-sweep lists)
-    int32_t nb[4];        // neighbour spins (== spin for self entries and unused columns),
-                          // table columns sorted by |J| descending
+    int32_t nb[4];        // neighbour spins (== nspins, the all-zero row, for self entries and unused
+                          // columns), table columns sorted by |J| descending
     float J[4];           // couplings (0 for unused columns), same order
     uint8_t dep[4];       // 0: nothing to wait for; 1: neighbour of a higher level (its previous sweep);
                           // 2: neighbour of a lower level (its current sweep)
@@ -78,7 +78,7 @@ struct piqmc_ctx {
 
     // packed state
     int nrows = 0, lanes = 0;
-    uint64_t *d_words = nullptr;    // [N][nrows]  (row fastest)
+    uint64_t *d_words = nullptr;    // [N + 1][nrows]  (row fastest); row N stays all-zero
     double *d_energy = nullptr;     // [nrows][lanes]
     void *d_stage = nullptr;        // grow-only staging buffer for host spins
     size_t stage_bytes = 0;
