@@ -36,10 +36,10 @@ GAMMA0, GAMMA1 = 1.5, 1e-8
 SEED = 2024
 B_ALG_HBM = 0.25        # bytes/attempt: each 64-slice word read once + written once per sweep
 B_ALG_SMEM = 1.0        # bytes/attempt touched on chip: own r+w, 4 neighbours, 2 Trotter bits
-# from the ncu captures under profiles/: DRAM bytes moved per sweep of this workload (read + write,
-# = the packed state once each way) and ALU-pipe (LOP3/SHF/IADD class) warp-instructions per attempt
-NCU_DRAM_BYTES_PER_SWEEP = 4.33e9
-NCU_ALU_WINST_PER_ATTEMPT = 0.205
+# from the ncu capture under profiles/r1_colour_sweep_fast_ncu.md: DRAM bytes moved per sweep of this
+# workload (read + write = the packed state once each way) and executed warp-instructions per attempt
+NCU_DRAM_BYTES_PER_SWEEP = 4.315e9
+NCU_WINST_PER_ATTEMPT = 0.187
 METRIC = "spin-flip attempts/sec"
 
 
@@ -314,14 +314,15 @@ def run_ours(args):
                      "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
                      "traffic": NCU_DRAM_BYTES_PER_SWEEP * K / launches / world,
                      "peak_source": pk_kind, "bytes_per_attempt": B_ALG_HBM,
-                     "note": "ALU-pipe-bound kernel (~6 logic instructions per attempt, no contraction): the HBM "
-                             "fraction is low by construction, traffic (ncu, bytes per launch) equals the "
-                             "algorithmic bytes; see roofline_alu and DESIGN.md section 4"},
-        "roofline_alu": {"bound": "alu_pipe", "achieved": NCU_ALU_WINST_PER_ATTEMPT * value / world / 1e9,
-                         "peak": nsm * 4 * 0.5 * sm_mhz * 1e6 / 1e9, "unit": "G warp-inst/s",
-                         "frac": NCU_ALU_WINST_PER_ATTEMPT * value / world / (nsm * 4 * 0.5 * sm_mhz * 1e6),
-                         "peak_source": "%d SMs x 4 SMSP x 0.5 warp-inst/clk (integer/logic pipe) x %.0f MHz" % (nsm, sm_mhz),
-                         "alu_warp_inst_per_attempt": NCU_ALU_WINST_PER_ATTEMPT},
+                     "note": "instruction-issue-bound kernel (~6 thread-instructions per attempt, no contraction): "
+                             "the HBM fraction is low by construction, traffic (ncu, bytes per launch) equals the "
+                             "algorithmic bytes; see roofline_issue and DESIGN.md section 4"},
+        "roofline_issue": {"bound": "issue_slots", "achieved": NCU_WINST_PER_ATTEMPT * value / world / 1e9,
+                           "peak": nsm * 4 * sm_mhz * 1e6 / 1e9, "unit": "G warp-inst/s",
+                           "frac": NCU_WINST_PER_ATTEMPT * value / world / (nsm * 4 * sm_mhz * 1e6),
+                           "peak_source": "%d SMs x 4 schedulers x 1 warp-inst/clk x %.0f MHz" % (nsm, sm_mhz),
+                           "warp_inst_per_attempt": NCU_WINST_PER_ATTEMPT,
+                           "note": "what binds this kernel: ncu shows 75% of the issue slots used, ALU pipe 63%"},
         "roofline_smem": {"achieved": B_ALG_SMEM * value / world / 1e9, "peak": smem_peak, "unit": "GB/s",
                           "frac": B_ALG_SMEM * value / world / 1e9 / smem_peak,
                           "bytes_per_attempt": B_ALG_SMEM, "peak_source": "128 B/clk/SM x %d SMs x %.0f MHz" % (nsm, sm_mhz)},
