@@ -779,7 +779,12 @@ int piqmc_state_replicas_to_slices(piqmc_handle h, int nreplicas, int slices)
     const int src_rows = h->nrows;
     uint64_t *dst = nullptr;
     PIQMC_CUDA(cudaMalloc(&dst, (size_t)nreplicas * (h->nspins + 1) * sizeof(uint64_t)));   // + the zero row
-    cudaMemsetAsync(dst + (size_t)nreplicas * h->nspins, 0, (size_t)nreplicas * sizeof(uint64_t), h->stream);
+    if (cudaMemsetAsync(dst + (size_t)nreplicas * h->nspins, 0, (size_t)nreplicas * sizeof(uint64_t), h->stream) !=
+        cudaSuccess) {
+        cudaFree(dst);
+        piqmc_set_error("cudaMemsetAsync failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return PIQMC_ECUDA;
+    }
     int rc = launch_replicas_to_slices(h, src, src_rows, dst, nreplicas, slices);
     cudaError_t e = cudaStreamSynchronize(h->stream);
     if (rc != PIQMC_OK || e != cudaSuccess) {
