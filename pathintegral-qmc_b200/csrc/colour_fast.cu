@@ -22,270 +22,9 @@
 // oracle_sa_colour (oracle/piqmc_oracle.c part 3), bit for bit.
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "colour_device.cuh"
 
 namespace {
-
-constexpr int FAST_THREADS = 128;
-constexpr int FAST_WARPS = FAST_THREADS / 32;
-constexpr int QCAP = 64;            // pooled draw requests per warp and pass
-constexpr int COOP_MIN = 4;         // words with at least this many needy lanes are drawn by the whole warp
-
-__device__ __forceinline__ float flip_sign(float negJ2, uint32_t bit)
-{
-    return __int_as_float(__float_as_int(negJ2) ^ (int)(bit << 31));
-}
-
-__device__ __forceinline__ uint32_t pick(const u32x4 &r, int q)
-{
-    return q == 0 ? r.x : (q == 1 ? r.y : (q == 2 ? r.z : r.w));
-}
-
-// the uniform of (row, lane, spin, sweep): Philox block (spin, lane>>2, sweep, row), word lane&3
-__device__ __forceinline__ uint32_t lane_uniform(int lane, uint32_t spin, uint32_t sweep, uint32_t prow,
-                                                 uint32_t k0, uint32_t k1)
-{
-    return pick(philox4x32_10(spin, (uint32_t)(lane >> 2) | (PIQMC_STREAM_SWEEP << 16), sweep, prow, k0, k1),
-                lane & 3);
-}
-
-// ---- the decision functions by name -----------------------------------------------------------
-// In the variables z_k = (disagreement with the neighbour of the k-th largest |J|) ^ (J < 0) the
-// energy difference is sum_k |2 J_k| (2 z_k - 1) + const, so "accept by sign" and "accept by sign
-// or needs a uniform" are monotone in every z_k and z_j dominates z_k for j < k: *regular*
-// functions, of which there are exactly 27 on 4 variables.  Truth table bit p, p = z0|z1<<1|z2<<2|z3<<3.
-#include "canon_eval.inc"   // generated by gen_canon.py: PIQMC_CANON_TABLES, PIQMC_CANON_EVAL_ASM
-constexpr uint32_t FID_GENERIC = 255u;   // not in the list (float rounding broke a dominance): pattern loop
-constexpr uint32_t FID_NONE = 254u;      // "needs a uniform" is identically false: skipped
-
-__constant__ uint32_t c_canon[32] = {PIQMC_CANON_TABLES, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu,
-                                     0xFFFFFFFFu};
-
-// any truth table: OR over its true patterns of the pattern's indicator (rare path, kept small)
-__device__ __noinline__ uint64_t eval_generic(uint32_t h, uint64_t z0, uint64_t z1, uint64_t z2, uint64_t z3)
-{
-    uint64_t r = 0ull;
-#pragma unroll 1
-    for (int p = 0; p < 16; p++)
-        if ((h >> p) & 1u) {
-            const uint64_t m0 = (p & 1) ? z0 : ~z0, m1 = (p & 2) ? z1 : ~z1;
-            const uint64_t m2 = (p & 4) ? z2 : ~z2, m3 = (p & 8) ? z3 : ~z3;
-            r |= m0 & m1 & m2 & m3;
-        }
-    return r;
-}
-
-// function `fid` (block-uniform) of the 4 masks, all 64 lanes at once: one indexed jump and at most
-// 3 LOP3 per 32 lanes.  *h is the truth table, read only on the generic path.
-__device__ __forceinline__ uint64_t eval_fn(uint32_t fid, const uint32_t *h, const uint64_t (&z)[4])
-{
-    uint32_t lo, hi;
-    if (fid < PIQMC_NCANON) {
-        asm(PIQMC_CANON_EVAL_ASM
-            : "=&r"(lo), "=&r"(hi)
-            : "r"(fid), "r"((uint32_t)z[0]), "r"((uint32_t)z[1]), "r"((uint32_t)z[2]), "r"((uint32_t)z[3]),
-              "r"((uint32_t)(z[0] >> 32)), "r"((uint32_t)(z[1] >> 32)), "r"((uint32_t)(z[2] >> 32)),
-              "r"((uint32_t)(z[3] >> 32)));
-    } else {
-        const uint64_t r = eval_generic(*h, z[0], z[1], z[2], z[3]);
-        lo = (uint32_t)r;
-        hi = (uint32_t)(r >> 32);
-    }
-    return ((uint64_t)hi << 32) | lo;
-}
-
-struct SpinTable {
-    uint32_t thr[3][16];     // acceptance threshold of z-pattern p in Trotter class c
-    uint32_t hacc[3];        // truth table (bit p) of "accept by sign", per Trotter class
-    uint32_t hall[3];        // ... of "accept by sign or needs a uniform"
-    uint32_t facc[3], fall[3];   // their names in the list (FID_GENERIC: not listed; fall FID_NONE: hall == hacc)
-    // the same, packed for the sweep loop (one 64-bit load each):
-    uint8_t names[8];        // byte 2c = facc[c], byte 2c+1 = fall[c]
-    uint16_t lane1[4];       // hacc[0], hacc[1], hall[0], hall[1]: all lane 1 ever needs (its class is 0 or 1)
-    float insum[16];         // in-slice energy difference of table-order pattern p: world-line moves
-};
-
-// Per-spin decision tables, built by warp c for Trotter class c without any block barrier
-// (the caller synchronises once).  Trotter class of a lane = number of Trotter neighbours it
-// disagrees with (0,1,2): tsum = -2*jp2, +0, +2*jp2.  Jz/pad: the record's sorted columns.
-template <bool QA>
-__device__ __forceinline__ void build_table_warp(SpinTable &tab, int c, const float (&Jz)[4], uint32_t pad,
-                                                 float jp2, float invT, bool force_generic)
-{
-    const int lane = threadIdx.x & 31;
-    const uint32_t p = lane & 15;                // z-pattern; lanes 16..31 mirror lanes 0..15
-    // the energy is summed in TABLE order (the specification's rounding sequence): table column n
-    // sits at sorted position k, its disagreement bit is z_k ^ sign_k
-    float e = 0.0f, ex = 0.0f;
-#pragma unroll
-    for (int n = 0; n < 4; n++) {                // unused columns carry J = 0: adding +-0 changes nothing
-        float Jn = 0.0f;
-        uint32_t bit = 0u;
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-            if (((pad >> (2 * k)) & 3u) == (uint32_t)n) {
-                Jn = Jz[k];
-                bit = ((p >> k) ^ (pad >> (8 + k))) & 1u;
-            }
-        e = __fadd_rn(e, flip_sign(-2.0f * Jn, bit));
-        ex = __fadd_rn(ex, flip_sign(-2.0f * Jn, (p >> n) & 1u));
-    }
-    if (c == 0 && lane < 16) tab.insum[p] = ex;
-    if (QA) {
-        const float tsum = (c == 0) ? -2.0f * jp2 : (c == 1 ? 0.0f : 2.0f * jp2);   // exact
-        e = __fadd_rn(e, tsum);
-    }
-    e = __fadd_rn(e, 0.0f);
-    const bool acc = QA ? (e > 0.0f) : (e >= 0.0f);
-    const float x = __fmul_rn(e, invT);
-    const bool need = !acc && (x >= PIQMC_XCUT);
-    if (lane < 16) tab.thr[c][p] = need ? colour_thresh(x) : 0u;
-    const uint32_t ha = __ballot_sync(0xffffffffu, acc) & 0xFFFFu;     // truth tables (bit p)
-    const uint32_t hb = __ballot_sync(0xffffffffu, acc || need) & 0xFFFFu;
-    const uint32_t name = c_canon[lane];
-    const uint32_t ma = __ballot_sync(0xffffffffu, name == ha), mb = __ballot_sync(0xffffffffu, name == hb);
-    if (lane == 0) {
-        const uint32_t fa = (ma && !force_generic) ? (uint32_t)(__ffs(ma) - 1) : FID_GENERIC;
-        const uint32_t fb = (hb == ha) ? FID_NONE : ((mb && !force_generic) ? (uint32_t)(__ffs(mb) - 1) : FID_GENERIC);
-        tab.hacc[c] = ha;
-        tab.hall[c] = hb;
-        tab.facc[c] = fa;
-        tab.fall[c] = fb;
-        tab.names[2 * c] = (uint8_t)fa;
-        tab.names[2 * c + 1] = (uint8_t)fb;
-        if (c < 2) {
-            tab.lane1[c] = (uint16_t)ha;
-            tab.lane1[2 + c] = (uint16_t)hb;
-        }
-    }
-}
-
-__device__ __forceinline__ uint32_t pattern_at(const uint64_t (&x)[4], int k)
-{
-    return (uint32_t)((x[0] >> k) & 1) | (uint32_t)((x[1] >> k) & 1) << 1 |
-           (uint32_t)((x[2] >> k) & 1) << 2 | (uint32_t)((x[3] >> k) & 1) << 3;
-}
-
-__device__ __forceinline__ uint64_t shfl64(uint64_t v, int src)
-{
-    const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src);
-    const uint32_t hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src);
-    return ((uint64_t)hi << 32) | lo;
-}
-
-// Resolve the lanes in NEED (those whose Metropolis test needs a uniform); returns the accepted
-// ones.  Must be called by all 32 threads of a warp.  Needy lanes cluster: the slices of one
-// replica are strongly correlated, so a word has either none or most of its 64 lanes needy.
-//   (a) a word with >= COOP_MIN needy lanes is broadcast to the warp; thread l draws slices
-//       2l and 2l+1 (one Philox block), results come back by warp OR-reduction;
-//   (b) the remaining scattered lanes are pooled in a per-warp queue and drawn 32 at a time.
-// All loops have warp-uniform trip counts (a per-thread `while (mask)` would make the hardware
-// run the threads' iterations one after another).
-template <bool QA>
-__device__ __forceinline__ uint64_t resolve_draws(uint64_t NEED, const uint64_t (&x)[4], uint64_t XL, uint64_t XR,
-                                                  const SpinTable &tab, uint2 *queue, uint32_t spin,
-                                                  uint32_t sweep, uint32_t prow_warp, uint32_t k0, uint32_t k1)
-{
-    const int lane = threadIdx.x & 31;
-    uint64_t ACC = 0;
-    uint32_t big = __ballot_sync(0xffffffffu, __popcll(NEED) >= COOP_MIN);
-    while (big) {                                                   // warp-uniform
-        const int src = __ffs(big) - 1;
-        big &= big - 1;
-        const uint64_t needs = shfl64(NEED, src);
-        uint64_t xs[4];
-#pragma unroll
-        for (int n = 0; n < 4; n++) xs[n] = shfl64(x[n], src);
-        const uint64_t xls = QA ? shfl64(XL, src) : 0ull, xrs = QA ? shfl64(XR, src) : 0ull;
-        const int ka = 2 * lane;
-        const uint32_t need2 = (uint32_t)(needs >> ka) & 3u;
-        uint32_t acc2 = 0;
-        if (need2) {
-            const u32x4 r = philox4x32_10(spin, (uint32_t)(ka >> 2) | (PIQMC_STREAM_SWEEP << 16), sweep,
-                                          prow_warp + (uint32_t)src, k0, k1);
-#pragma unroll
-            for (int b = 0; b < 2; b++) {
-                const int k = ka + b;
-                const uint32_t c = QA ? (uint32_t)((xls >> k) & 1) + (uint32_t)((xrs >> k) & 1) : 0u;
-                const uint32_t u = (ka & 2) ? (b ? r.w : r.z) : (b ? r.y : r.x);
-                if (((need2 >> b) & 1u) && u < tab.thr[c][pattern_at(xs, k)]) acc2 |= 1u << b;
-            }
-        }
-        const uint32_t lo = __reduce_or_sync(0xffffffffu, lane < 16 ? acc2 << (2 * lane) : 0u);
-        const uint32_t hi = __reduce_or_sync(0xffffffffu, lane >= 16 ? acc2 << (2 * lane - 32) : 0u);
-        if (lane == src) {
-            ACC |= ((uint64_t)hi << 32) | lo;
-            NEED = 0;
-        }
-    }
-    while (true) {
-        const int n = __popcll(NEED);
-        int incl = n;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += t;
-        }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        if (total == 0) break;
-        const int excl = incl - n;
-        uint64_t mask = NEED;
-        int pos = excl;
-#pragma unroll
-        for (int j = 0; j < COOP_MIN - 1; j++) {                    // n < COOP_MIN here
-            if (mask && pos < QCAP) {
-                const int k = __ffsll((long long)mask) - 1;
-                mask &= mask - 1;
-                const uint32_t c = QA ? (uint32_t)((XL >> k) & 1) + (uint32_t)((XR >> k) & 1) : 0u;
-                queue[pos++] = make_uint2(tab.thr[c][pattern_at(x, k)], (uint32_t)lane | ((uint32_t)k << 5));
-            }
-        }
-        const uint64_t taken = NEED ^ mask;
-        __syncwarp();
-        const int T = total < QCAP ? total : QCAP;
-        uint32_t res[QCAP / 32];
-#pragma unroll
-        for (int r = 0; r < QCAP / 32; r++) {
-            res[r] = 0u;
-            if (r * 32 < T) {                                       // warp-uniform
-                bool a = false;
-                const int it = r * 32 + lane;
-                if (it < T) {
-                    const uint2 q = queue[it];
-                    a = lane_uniform((int)(q.y >> 5), spin, sweep, prow_warp + (q.y & 31u), k0, k1) < q.x;
-                }
-                res[r] = __ballot_sync(0xffffffffu, a);
-            }
-        }
-        uint64_t tk = taken;
-        pos = excl;
-#pragma unroll
-        for (int j = 0; j < COOP_MIN - 1; j++) {
-            if (tk) {
-                const int k = __ffsll((long long)tk) - 1;
-                tk &= tk - 1;
-                const uint32_t word = (pos < 32) ? res[0] : res[QCAP / 32 - 1];
-                if ((word >> (pos & 31)) & 1u) ACC |= 1ull << k;
-                pos++;
-            }
-        }
-        NEED = mask;
-        __syncwarp();
-    }
-    return ACC;
-}
-
-__device__ __forceinline__ uint32_t ld_acquire(const uint32_t *p)
-{
-    uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
-__device__ __forceinline__ void st_release(uint32_t *p, uint32_t v)
-{
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 
 struct FastArgs {
     uint64_t *words;            // [N][nrows]
@@ -380,6 +119,7 @@ __global__ void __launch_bounds__(FAST_THREADS, MINB) colour_sweep_fast(const Fa
     const uint64_t fnames = *reinterpret_cast<const uint64_t *>(tab.names);
     const uint64_t lane1tab = *reinterpret_cast<const uint64_t *>(tab.lane1);
 
+    const auto thr_tab = [&](uint32_t c, uint32_t pat) -> uint32_t { return tab.thr[c][pat]; };
     const int rbeg = chunk * a.rows_per_block;
     const int rend = min(nrows, rbeg + a.rows_per_block);
     const uint64_t valid = (lanes >= 64) ? ~0ull : ((1ull << lanes) - 1ull);
@@ -479,7 +219,7 @@ __global__ void __launch_bounds__(FAST_THREADS, MINB) colour_sweep_fast(const Fa
                 if (fb != FID_NONE) NEED |= eval_fn(fb, &tab.hall[c], z) & ~V & Cc;
             }
             if (__any_sync(0xffffffffu, NEED != 0))
-                ACC |= resolve_draws<QA>(NEED, z, XL, XR, tab, queue, (uint32_t)i, sweep, prow_warp, a.k0, a.k1);
+                ACC |= resolve_draws<QA>(NEED, z, XL, XR, thr_tab, queue, (uint32_t)i, sweep, prow_warp, a.k0, a.k1);
             result = w ^ (uint64_t)flip1 ^ ACC;
         } else {
             // ---- periodic Trotter neighbours k-1, k+1: even slices first, then odd slices (the lanes
@@ -509,7 +249,7 @@ __global__ void __launch_bounds__(FAST_THREADS, MINB) colour_sweep_fast(const Fa
                 const uint64_t NEED = ((C0 & N[0]) | (C1 & N[1]) | (C2 & N[NC - 1])) & sel;
                 // lanes of this pass have not flipped yet, so their rows of z are still current
                 if (__any_sync(0xffffffffu, NEED != 0))
-                    ACC |= resolve_draws<QA>(NEED, z, XL, XR, tab, queue, (uint32_t)i, sweep, prow_warp, a.k0, a.k1);
+                    ACC |= resolve_draws<QA>(NEED, z, XL, XR, thr_tab, queue, (uint32_t)i, sweep, prow_warp, a.k0, a.k1);
                 cur ^= ACC;
             }
             result = cur;
