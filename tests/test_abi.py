@@ -87,3 +87,24 @@ def test_argument_validation_mirrors_reference_errors():
         qmc.QuantumAnneal(np.linspace(1, 0.1, 3), 1, 3, 0.1, 4, np.ones(4), nbs, np.random.RandomState(0))
     with pytest.raises(ValueError):
         sa.Anneal_multispin(np.linspace(1, 0.1, 3), 1, np.zeros((63, 4)), nbs, np.random.RandomState(0))
+
+
+def test_dense_wrappers_validate_like_cython_memoryviews():
+    """QuantumAnneal_dense / Anneal_dense take np.float_t[:, :] J (qmc.pyx:149, sa.pyx:133): float64
+    only, two dimensions, and the shapes must agree -- checked before any device is touched."""
+    import piqmc.qmc as qmc
+    import piqmc.sa as sa
+    rng = np.random.RandomState(0)
+    sched = np.linspace(1.0, 0.1, 3)
+    sv = np.ones(4)
+    with pytest.raises(ValueError):
+        sa.Anneal_dense(sched, 1, sv, np.zeros((4, 4), dtype=np.float32), rng)
+    with pytest.raises(ValueError):
+        sa.Anneal_dense(sched, 1, sv, np.zeros(16), rng)
+    with pytest.raises(ValueError):
+        sa.Anneal_dense(sched, 1, sv, np.zeros((5, 5)), rng)
+    confs = np.ones((4, 3))
+    with pytest.raises(ValueError):
+        qmc.QuantumAnneal_dense(sched, 1, 3, 0.1, 4, confs, np.zeros((4, 5)), rng)
+    with pytest.raises(ValueError):
+        qmc.QuantumAnneal_dense(sched, 1, 3, 0.1, 4, confs.astype(np.float32), np.zeros((4, 4)), rng)
