@@ -362,6 +362,13 @@ int piqmc_create(int device, piqmc_handle *out)
         delete c;
         return PIQMC_ECUDA;
     }
+    if (prop.major != 10) {                         // the kernels exist for sm_100a only: say so now, not at the first launch
+        piqmc_set_error("device %d is sm_%d%d; libpiqmc_b200 is built for sm_100a (B200) only", device, prop.major,
+                        prop.minor);
+        cudaStreamDestroy(c->stream);
+        delete c;
+        return PIQMC_ECUDA;
+    }
     c->sm_count = prop.multiProcessorCount;
     *out = c;
     return PIQMC_OK;
