@@ -40,6 +40,7 @@ struct FastArgs {
     unsigned int ticket_base;   // units handed out by earlier launches of the same run
     unsigned int poll_ns;       // back-off between polls of a completion flag (0 = spin)
     int force_generic;          // testing: evaluate every decision function by the generic pattern loop
+    uint64_t valid, top;        // lane masks: all `lanes` slices / the last slice (kernel constants: no per-pass arithmetic)
 };
 
 // MINB = resident blocks per SM the register allocation is capped for (7 -> 72 registers, 8 -> 64, 9 -> 56):
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(FAST_THREADS, MINB) colour_sweep_fast(const Fa
     const auto thr_tab = [&](uint32_t c, uint32_t pat) -> uint32_t { return tab.thr[c][pat]; };
     const int rbeg = chunk * a.rows_per_block;
     const int rend = min(nrows, rbeg + a.rows_per_block);
-    const uint64_t valid = (lanes >= 64) ? ~0ull : ((1ull << lanes) - 1ull);
+    const uint64_t valid = a.valid;
     uint2 *queue = queues[threadIdx.x >> 5];
     uint64_t *words = a.words;
 
@@ -179,9 +180,9 @@ __global__ void __launch_bounds__(FAST_THREADS, MINB) colour_sweep_fast(const Fa
                 // ---- reference Trotter neighbours: slices P-1 (old value for everyone; itself for lane
                 //      P-1) and 1 (old for lane 0, itself for lane 1, new for lanes >= 2): lane 1 is
                 //      decided first, straight from the truth tables.
-                const uint64_t bl = ((w >> (lanes - 1)) & 1ull) ? ~0ull : 0ull;
-                const uint64_t br_old = ((w >> 1) & 1ull) ? ~0ull : 0ull;
-                XL = (w ^ bl) & ~(1ull << (lanes - 1));
+                const uint64_t bl = (w & a.top) ? ~0ull : 0ull;
+                const uint64_t br_old = (w & 2ull) ? ~0ull : 0ull;
+                XL = (w ^ bl) & ~a.top;
                 const uint32_t c1 = (uint32_t)(XL >> 1) & 1u;               // right neighbour of lane 1 is itself
                 const uint32_t p1 = pattern_at(z, 1);
                 if (live) {
@@ -343,6 +344,8 @@ int launch_fast_sweeps(piqmc_ctx *c, int qa, int trotter, int nsweeps, const Piq
     a.nrows = c->nrows;
     a.maxnb = c->maxnb;
     a.lanes = c->lanes;
+    a.valid = (c->lanes >= 64) ? ~0ull : ((1ull << c->lanes) - 1ull);
+    a.top = 1ull << (c->lanes - 1);
     a.nchunks = nchunks;
     a.rows_per_block = rpb;
     a.per_sweep_lists = per_sweep_lists;
