@@ -130,12 +130,20 @@ def _cpu_job(args):
     if "qmc" in _G:
         if kind == "qa":
             _G["qmc"].QuantumAnneal(sched, 1, P, TEMP, n, confs, _G["nbs"], rng)
+        elif kind.startswith("qa_omp"):                      # the reference's OpenMP variant, all threads in one process
+            _G["qmc"].QuantumAnneal_parallel(sched, 1, P, TEMP, n, confs, _G["nbs"], int(kind[6:]))
+        elif kind == "sa":                                   # classical pre-anneal on one slice-sized vector, P sweeps
+            from piqmc_ref import sa as ref_sa
+            ref_sa.Anneal(np.linspace(3.0, 0.01, nsteps * P), 1, sv, _G["nbs"], rng)
         else:
             _G["qmc"].QuantumAnneal_parallel(sched, 1, P, TEMP, n, confs, _G["nbs"], 1)
     else:
         O = _G["O"]
         if kind == "qa":
             O.qa_reference(sched, 1, P, TEMP, n, confs, _G["nbs"], O.make_perms(rng, n, nsteps))
+        elif kind == "sa":
+            ssched = np.linspace(3.0, 0.01, nsteps * P)
+            O.sa_reference(ssched, 1, sv, _G["nbs"], O.make_perms(rng, n, ssched.size))
         else:
             O.qa_parallel1(sched, 1, P, TEMP, n, confs, _G["nbs"])
     return time.perf_counter() - t0
@@ -335,11 +343,15 @@ def run_ours(args):
         r_qa, w_qa, kind = cpu_rate(nbs, 3, "qa", cores)
         r_par, w_par, _ = cpu_rate(nbs, 3, "qa_par", cores)
         r_1, w_1, _ = cpu_rate(nbs, 3, "qa", 1)
+        r_omp, w_omp, _ = cpu_rate(nbs, 2, "qa_omp%d" % cores, 1)      # OpenMP variant: one process, all threads
+        r_sa, w_sa, _ = cpu_rate(nbs, 3, "sa", cores)                  # sa.Anneal, same number of attempts per job
         line["cpu_baseline"] = {
             "value": max(r_qa, r_par), "unit": "attempts/s", "cores": cores, "kind": kind,
             "sample": "%d replicas (one per core) x 3 sweeps of the same 256x256 P=64 workload" % cores,
             "qmc.QuantumAnneal": r_qa, "qmc.QuantumAnneal_parallel(nthreads=1)": r_par,
-            "qmc.QuantumAnneal_1core": r_1}
+            "qmc.QuantumAnneal_1core": r_1,
+            "qmc.QuantumAnneal_parallel(nthreads=%d) OpenMP, 1 process" % cores: r_omp,
+            "sa.Anneal (%d processes)" % cores: r_sa}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
