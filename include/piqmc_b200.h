@@ -145,11 +145,19 @@ float piqmc_jperp(double gamma, int slices, float temp);
  * Semantics are stated on the CPU in oracle/piqmc_oracle.c part 3 and reproduced bit-exactly.
  */
 int piqmc_state_alloc(piqmc_handle h, int nrows, int lanes);
+/* QA states with at most 32 slices: `per_word` replicas share a word, replica row*per_word + g in
+ * bits [g*slices, (g+1)*slices).  Results are those of the one-replica-per-word layout, replica by
+ * replica (same Philox keys); only the fast kernel with the reference Trotter neighbours runs on
+ * such a state.  slices must be a multiple of 4 when per_word > 1, slices*per_word <= 64.
+ * piqmc_state_upload_spins then takes nrows*per_word replicas; piqmc_energy returns
+ * energies[(row*per_word + g)*slices + k]; row0/replica0 arguments are replica ids. */
+int piqmc_state_alloc_packed(piqmc_handle h, int nrows, int slices, int per_word);
 /* Turn the resident SA state (64 replicas per word) into a QA state on the device: one row per
  * replica, every one of the `slices` lanes equal to the replica's spin -- the reference's
  * np.tile(spinVector, (P,1)).T hand-over from the SA pre-anneal to PIQMC
  * (examples/spinglass32.py:94-96,124-127). */
 int piqmc_state_replicas_to_slices(piqmc_handle h, int nreplicas, int slices);
+int piqmc_state_replicas_to_slices_packed(piqmc_handle h, int nreplicas, int slices, int per_word);
 /* random initial state from Philox: tile != 0 -> one bit per (row, spin) copied to every lane
  * (the reference's np.tile(spinVector,(P,1)).T start, examples/spinglass32.py:94-96);
  * tile == 0 -> independent bit per (row*64+lane, spin). */

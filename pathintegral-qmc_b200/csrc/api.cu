@@ -752,14 +752,28 @@ int piqmc_sa_multispin_det(piqmc_handle h, const double *sched, int nsched, int 
 }
 
 // ---- packed state ----------------------------------------------------------------------------
-int piqmc_state_alloc(piqmc_handle h, int nrows, int lanes)
+static int check_packing(int slices, int per_word)
+{
+    PIQMC_REQUIRE(per_word >= 1 && slices >= 1 && slices * per_word <= 64, PIQMC_EINVAL,
+                  "slices * per_word must be at most 64");
+    PIQMC_REQUIRE(per_word == 1 || (slices % 4 == 0 && slices >= 4), PIQMC_EINVAL,
+                  "several replicas per word need a slice count that is a multiple of 4 (a Philox block "
+                  "serves 4 consecutive slices of one replica)");
+    return PIQMC_OK;
+}
+
+int piqmc_state_alloc(piqmc_handle h, int nrows, int lanes) { return piqmc_state_alloc_packed(h, nrows, lanes, 1); }
+
+int piqmc_state_alloc_packed(piqmc_handle h, int nrows, int slices, int per_word)
 {
     USE(h);
     PIQMC_REQUIRE(h->nspins > 0, PIQMC_ENOGRAPH, "piqmc_set_graph has not been called");
     PIQMC_REQUIRE(nrows > 0 && nrows <= 65535, PIQMC_EINVAL, "nrows must be in [1, 65535]");
-    PIQMC_REQUIRE(lanes >= 1 && lanes <= 64, PIQMC_EINVAL,
+    PIQMC_REQUIRE(slices >= 1 && slices <= 64, PIQMC_EINVAL,
                   "lanes must be in [1, 64] (the packed path holds all slices of a spin in one 64-bit word)");
-    if (h->d_words && h->nrows == nrows && h->lanes == lanes) {
+    TRY(check_packing(slices, per_word));
+    const int lanes = slices * per_word;
+    if (h->d_words && h->nrows == nrows && h->lanes == lanes && h->seg_P == slices && h->seg_S == per_word) {
         // same shape: keep the buffers (and the dataflow flags, which are consistent between runs)
         PIQMC_CUDA(cudaMemsetAsync(h->d_words, 0, (size_t)nrows * h->nspins * sizeof(uint64_t), h->stream));
         return PIQMC_OK;
@@ -772,27 +786,37 @@ int piqmc_state_alloc(piqmc_handle h, int nrows, int lanes)
     PIQMC_CUDA(cudaMemsetAsync(h->d_words, 0, (size_t)nrows * (h->nspins + 1) * sizeof(uint64_t), h->stream));
     h->nrows = nrows;
     h->lanes = lanes;
+    h->seg_P = slices;
+    h->seg_S = per_word;
     return PIQMC_OK;
 }
 
 int piqmc_state_replicas_to_slices(piqmc_handle h, int nreplicas, int slices)
 {
+    return piqmc_state_replicas_to_slices_packed(h, nreplicas, slices, 1);
+}
+
+int piqmc_state_replicas_to_slices_packed(piqmc_handle h, int nreplicas, int slices, int per_word)
+{
     USE(h);
-    PIQMC_REQUIRE(h->d_words && h->lanes == 64, PIQMC_ENOSTATE, "no resident SA state (64 replicas per word)");
-    PIQMC_REQUIRE(nreplicas > 0 && nreplicas <= h->nrows * 64 && nreplicas <= 65535, PIQMC_EINVAL,
-                  "nreplicas must be in [1, min(64*rows, 65535)]");
+    PIQMC_REQUIRE(h->d_words && h->lanes == 64 && h->seg_S == 1, PIQMC_ENOSTATE,
+                  "no resident SA state (64 replicas per word)");
+    PIQMC_REQUIRE(nreplicas > 0 && nreplicas <= h->nrows * 64, PIQMC_EINVAL, "nreplicas must be in [1, 64*rows]");
     PIQMC_REQUIRE(slices >= 2 && slices <= 64, PIQMC_EINVAL, "slices must be in [2, 64]");
+    TRY(check_packing(slices, per_word));
+    const int dst_rows = (nreplicas + per_word - 1) / per_word;
+    PIQMC_REQUIRE(dst_rows <= 65535, PIQMC_EINVAL, "too many rows");
     uint64_t *src = h->d_words;
     const int src_rows = h->nrows;
     uint64_t *dst = nullptr;
-    PIQMC_CUDA(cudaMalloc(&dst, (size_t)nreplicas * (h->nspins + 1) * sizeof(uint64_t)));   // + the zero row
-    if (cudaMemsetAsync(dst + (size_t)nreplicas * h->nspins, 0, (size_t)nreplicas * sizeof(uint64_t), h->stream) !=
+    PIQMC_CUDA(cudaMalloc(&dst, (size_t)dst_rows * (h->nspins + 1) * sizeof(uint64_t)));   // + the zero row
+    if (cudaMemsetAsync(dst + (size_t)dst_rows * h->nspins, 0, (size_t)dst_rows * sizeof(uint64_t), h->stream) !=
         cudaSuccess) {
         cudaFree(dst);
         piqmc_set_error("cudaMemsetAsync failed: %s", cudaGetErrorString(cudaGetLastError()));
         return PIQMC_ECUDA;
     }
-    int rc = launch_replicas_to_slices(h, src, src_rows, dst, nreplicas, slices);
+    int rc = launch_replicas_to_slices(h, src, src_rows, dst, dst_rows, nreplicas, slices, per_word);
     cudaError_t e = cudaStreamSynchronize(h->stream);
     if (rc != PIQMC_OK || e != cudaSuccess) {
         cudaFree(dst);
@@ -801,9 +825,11 @@ int piqmc_state_replicas_to_slices(piqmc_handle h, int nreplicas, int slices)
     }
     free_state(h);
     h->d_words = dst;
-    PIQMC_CUDA(cudaMalloc(&h->d_energy, (size_t)nreplicas * slices * sizeof(double)));
-    h->nrows = nreplicas;
-    h->lanes = slices;
+    PIQMC_CUDA(cudaMalloc(&h->d_energy, (size_t)dst_rows * slices * per_word * sizeof(double)));
+    h->nrows = dst_rows;
+    h->lanes = slices * per_word;
+    h->seg_P = slices;
+    h->seg_S = per_word;
     return PIQMC_OK;
 }
 
@@ -819,7 +845,7 @@ int piqmc_state_upload_spins(piqmc_handle h, const int8_t *spins, int tile)
     USE(h);
     PIQMC_REQUIRE(h->d_words, PIQMC_ENOSTATE, "no packed state (call piqmc_state_alloc)");
     PIQMC_REQUIRE(spins, PIQMC_EINVAL, "null spins");
-    const size_t n = (size_t)h->nrows * h->nspins * (tile ? 1 : h->lanes);
+    const size_t n = (size_t)h->nrows * h->seg_S * h->nspins * (tile ? 1 : h->seg_P);   // nrows*seg_S replicas
     if (n > h->stage_bytes) {                       // grow-only staging buffer: no malloc/free per call
         PIQMC_CUDA(cudaStreamSynchronize(h->stream));
         free_dev(h->d_stage);
@@ -880,12 +906,16 @@ int piqmc_qa_colour(piqmc_handle h, const double *sched, int nsched, int mcsteps
     PIQMC_REQUIRE(h->d_words, PIQMC_ENOSTATE, "no packed state (call piqmc_state_alloc)");
     PIQMC_REQUIRE(sched && nsched >= 0 && mcsteps >= 0, PIQMC_EINVAL, "bad schedule");
     PIQMC_REQUIRE(trotter == 0 || trotter == 1, PIQMC_EINVAL, "trotter must be 0 or 1");
-    PIQMC_REQUIRE(h->lanes >= 2, PIQMC_EINVAL, "slices must be >= 2");
-    PIQMC_REQUIRE((float)h->lanes * temp != 0.0f && temp != 0.0f, PIQMC_EZERODIV, "float division");
+    const int slices = h->seg_P;                    // per replica (several replicas may share a word)
+    PIQMC_REQUIRE(slices >= 2, PIQMC_EINVAL, "slices must be >= 2");
+    PIQMC_REQUIRE((float)slices * temp != 0.0f && temp != 0.0f, PIQMC_EZERODIV, "float division");
     PIQMC_REQUIRE(!h->global_moves || piqmc_fast_ok(h, 1, trotter), PIQMC_EINVAL,
                   "world-line moves need the table kernel (maxnb <= 4, variant != 1, >= 32 rows)");
+    PIQMC_REQUIRE(h->seg_S == 1 || (piqmc_fast_ok(h, 1, trotter) && trotter == 0 && !h->global_moves), PIQMC_EINVAL,
+                  "several replicas per word need the table kernel (maxnb <= 4, variant != 1, >= 32 rows), the "
+                  "reference Trotter neighbours and no world-line moves");
     std::vector<float> jp2(std::max(nsched, 1)), invT(std::max(nsched, 1), 1.0f / temp);
-    for (int f = 0; f < nsched; f++) jp2[f] = 2.0f * piqmc_jperp(sched[f], h->lanes, temp);
+    for (int f = 0; f < nsched; f++) jp2[f] = 2.0f * piqmc_jperp(sched[f], slices, temp);
     return run_colour_sweeps(h, 1, trotter, nsched, mcsteps, jp2, invT, seed, replica0, sweep0, orders);
 }
 
@@ -895,6 +925,7 @@ int piqmc_sa_colour(piqmc_handle h, const double *sched, int nsched, int mcsteps
     USE(h);
     PIQMC_REQUIRE(h->d_words, PIQMC_ENOSTATE, "no packed state (call piqmc_state_alloc)");
     PIQMC_REQUIRE(sched && nsched >= 0 && mcsteps >= 0, PIQMC_EINVAL, "bad schedule");
+    PIQMC_REQUIRE(h->seg_S == 1, PIQMC_EINVAL, "the SA sweeps work on states with one group of 64 replicas per word");
     std::vector<float> jp2(std::max(nsched, 1), 0.0f), invT(std::max(nsched, 1));
     for (int t = 0; t < nsched; t++) invT[t] = 1.0f / (float)sched[t];
     return run_colour_sweeps(h, 0, 0, nsched, mcsteps, jp2, invT, seed, row0, sweep0, orders);

@@ -41,12 +41,16 @@ struct FastArgs {
     unsigned int poll_ns;       // back-off between polls of a completion flag (0 = spin)
     int force_generic;          // testing: evaluate every decision function by the generic pattern loop
     uint64_t valid, top;        // lane masks: all `lanes` slices / the last slice (kernel constants: no per-pass arithmetic)
+    // several replicas per word (SEG): seg_S segments of seg_P lanes; masks of the first, second and last lane of
+    // every segment, and of one whole segment
+    int seg_P, seg_S;
+    uint64_t seg_low, seg_l1, seg_top, seg_ones;
 };
 
 // MINB = resident blocks per SM the register allocation is capped for (7 -> 72 registers, 8 -> 64, 9 -> 56):
 // more resident blocks hide the per-unit latencies (ticket, record, flags) better, which matters
 // most when a unit has little work (few rows).
-template <bool QA, int TROT, int MINB>
+template <bool QA, int TROT, int MINB, bool SEG = false>
 __global__ void __launch_bounds__(FAST_THREADS, MINB) colour_sweep_fast(const FastArgs a)
 {
     __shared__ SpinTable tab;
@@ -162,7 +166,7 @@ __global__ void __launch_bounds__(FAST_THREADS, MINB) colour_sweep_fast(const Fa
                     wn_nx[n] = __ldcg(words + (size_t)nb[n] * nrows + rown);
             }
         }
-        const uint32_t prow_warp = a.row0 + (uint32_t)(base + (threadIdx.x & ~31));
+        const uint32_t prow_warp = a.row0 + (uint32_t)(base + (threadIdx.x & ~31)) * (SEG ? (uint32_t)a.seg_S : 1u);
 
         // "accept by sign" and "accept by sign or needs a uniform" of every Trotter class for all 64
         // lanes at once, by name (fnames byte 2c / 2c+1), through two evaluation sites in a rolled
@@ -171,11 +175,48 @@ __global__ void __launch_bounds__(FAST_THREADS, MINB) colour_sweep_fast(const Fa
         uint64_t result;
         if (!QA || TROT == 0) {
             uint64_t C[3], todo, XL = 0ull, XR = 0ull;
-            uint32_t flip1 = 0u;
+            uint64_t flip1 = 0ull;
             if (!QA) {
                 // ---- SA: no Trotter terms, one class
                 todo = live ? valid : 0ull;
                 C[0] = C[1] = C[2] = todo;
+            } else if (SEG) {
+                // ---- several replicas per word: the same rules segment by segment.  The last slice
+                //      and slice 1 of every segment are broadcast over their segment by a multiplication
+                //      (the products of the segments' base bits with 2^P - 1 do not overlap).
+                const uint64_t ones = a.seg_ones;
+                const uint64_t bl = ((w & a.seg_top) >> (a.seg_P - 1)) * ones;
+                const uint64_t br_old = ((w & a.seg_l1) >> 1) * ones;
+                XL = (w ^ bl) & ~a.seg_top;
+                // slice 1 of every segment first (its right neighbour is itself: class = left bit),
+                // straight from the decision functions of classes 0 and 1
+                const uint32_t fa0 = (uint32_t)fnames & 0xFFu, fb0 = (uint32_t)(fnames >> 8) & 0xFFu;
+                const uint32_t fa1 = (uint32_t)(fnames >> 16) & 0xFFu, fb1 = (uint32_t)(fnames >> 24) & 0xFFu;
+                const uint64_t F0 = eval_fn(fa0, &tab.hacc[0], z);
+                const uint64_t F1 = (fa1 == fa0 && fa0 != FID_GENERIC) ? F0 : eval_fn(fa1, &tab.hacc[1], z);
+                uint64_t N0 = 0ull, N1 = 0ull;
+                if (fb0 != FID_NONE) N0 = eval_fn(fb0, &tab.hall[0], z) & ~F0;
+                if (fb1 != FID_NONE) N1 = eval_fn(fb1, &tab.hall[1], z) & ~F1;
+                const uint64_t l1 = live ? a.seg_l1 : 0ull;
+                flip1 = ((XL & F1) | (~XL & F0)) & l1;
+                const uint64_t need1 = ((XL & N1) | (~XL & N0)) & l1;
+                if (__any_sync(0xffffffffu, need1 != 0ull)) {            // ~1% of the words
+                    for (int g = 0; g < a.seg_S; g++) {                  // warp-uniform trip count
+                        const int k = g * a.seg_P + 1;
+                        if ((need1 >> k) & 1ull) {
+                            const uint32_t c1 = (uint32_t)(XL >> k) & 1u;
+                            if (lane_uniform(1, (uint32_t)i, sweep, a.row0 + (uint32_t)(row * a.seg_S + g), a.k0, a.k1) <
+                                tab.thr[c1][pattern_at(z, k)])
+                                flip1 |= 1ull << k;
+                        }
+                    }
+                }
+                const uint64_t br_new = (((w ^ flip1) & a.seg_l1) >> 1) * ones;
+                XR = ((w ^ br_new) & ~a.seg_low) | ((w ^ br_old) & a.seg_low);   // slice 0 sees the old slice 1
+                todo = live ? (valid & ~a.seg_l1) : 0ull;
+                C[0] = ~(XL | XR) & todo;
+                C[1] = (XL ^ XR) & todo;
+                C[2] = (XL & XR) & todo;
             } else {
                 // ---- reference Trotter neighbours: slices P-1 (old value for everyone; itself for lane
                 //      P-1) and 1 (old for lane 0, itself for lane 1, new for lanes >= 2): lane 1 is
@@ -188,10 +229,10 @@ __global__ void __launch_bounds__(FAST_THREADS, MINB) colour_sweep_fast(const Fa
                 if (live) {
                     const uint32_t t1 = (uint32_t)(lane1tab >> (16u * c1 + p1));    // bit 0: accept, bit 32: accept or need
                     const uint32_t t2 = (uint32_t)(lane1tab >> (32u + 16u * c1 + p1));
-                    if (t1 & 1u) flip1 = 2u;
+                    if (t1 & 1u) flip1 = 2ull;
                     else if (t2 & 1u)                                        // ~1% of the words
                         if (lane_uniform(1, (uint32_t)i, sweep, a.row0 + (uint32_t)row, a.k0, a.k1) < tab.thr[c1][p1])
-                            flip1 = 2u;
+                            flip1 = 2ull;
                 }
                 const uint64_t br_new = br_old ^ (flip1 ? ~0ull : 0ull);
                 XR = ((w ^ br_new) & ~1ull) | ((w ^ br_old) & 1ull);        // lane 0 sees the old bit 1
@@ -220,8 +261,9 @@ __global__ void __launch_bounds__(FAST_THREADS, MINB) colour_sweep_fast(const Fa
                 if (fb != FID_NONE) NEED |= eval_fn(fb, &tab.hall[c], z) & ~V & Cc;
             }
             if (__any_sync(0xffffffffu, NEED != 0))
-                ACC |= resolve_draws<QA>(NEED, z, XL, XR, thr_tab, queue, (uint32_t)i, sweep, prow_warp, a.k0, a.k1);
-            result = w ^ (uint64_t)flip1 ^ ACC;
+                ACC |= resolve_draws<QA>(NEED, z, XL, XR, thr_tab, queue, (uint32_t)i, sweep, prow_warp, a.k0, a.k1,
+                                         SEG ? a.seg_P : 64, SEG ? a.seg_S : 1);
+            result = w ^ flip1 ^ ACC;
         } else {
             // ---- periodic Trotter neighbours k-1, k+1: even slices first, then odd slices (the lanes
             //      of one pass do not see each other).  With an odd slice count lanes 0 and P-1 are
@@ -346,6 +388,15 @@ int launch_fast_sweeps(piqmc_ctx *c, int qa, int trotter, int nsweeps, const Piq
     a.lanes = c->lanes;
     a.valid = (c->lanes >= 64) ? ~0ull : ((1ull << c->lanes) - 1ull);
     a.top = 1ull << (c->lanes - 1);
+    a.seg_P = c->seg_P;
+    a.seg_S = c->seg_S;
+    a.seg_low = a.seg_l1 = a.seg_top = 0ull;
+    a.seg_ones = (c->seg_P >= 64) ? ~0ull : ((1ull << c->seg_P) - 1ull);
+    for (int g = 0; g < c->seg_S; g++) {
+        a.seg_low |= 1ull << (g * c->seg_P);
+        a.seg_l1 |= 2ull << (g * c->seg_P);
+        a.seg_top |= 1ull << (g * c->seg_P + c->seg_P - 1);
+    }
     a.nchunks = nchunks;
     a.rows_per_block = rpb;
     a.per_sweep_lists = per_sweep_lists;
@@ -382,7 +433,8 @@ int launch_fast_sweeps(piqmc_ctx *c, int qa, int trotter, int nsweeps, const Piq
             if (minb == 7) colour_sweep_fast<true, 1, 7><<<grid, block, 0, c->stream>>>(a);
             else           colour_sweep_fast<true, 1, 8><<<grid, block, 0, c->stream>>>(a);
         } else {
-            if (minb == 7)       colour_sweep_fast<true, 0, 7><<<grid, block, 0, c->stream>>>(a);
+            if (c->seg_S > 1)    colour_sweep_fast<true, 0, 8, true><<<grid, block, 0, c->stream>>>(a);
+            else if (minb == 7)  colour_sweep_fast<true, 0, 7><<<grid, block, 0, c->stream>>>(a);
             else if (minb == 9)  colour_sweep_fast<true, 0, 9><<<grid, block, 0, c->stream>>>(a);
             else if (minb == 10) colour_sweep_fast<true, 0, 10><<<grid, block, 0, c->stream>>>(a);
             else                 colour_sweep_fast<true, 0, 8><<<grid, block, 0, c->stream>>>(a);

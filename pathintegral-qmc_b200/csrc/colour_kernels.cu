@@ -110,16 +110,21 @@ __global__ void __launch_bounds__(128) colour_sweep_generic(
 // ------------------------------------------------------------------------------------------
 // state initialisation / packing
 // ------------------------------------------------------------------------------------------
-__global__ void state_init_kernel(uint64_t *words, int nspins, int nrows, int lanes, uint32_t k0,
-                                  uint32_t k1, uint32_t row0, int tile)
+// all lanes of a segment of P lanes
+__device__ __forceinline__ uint64_t seg_ones(int P) { return (P >= 64) ? ~0ull : ((1ull << P) - 1ull); }
+
+__global__ void state_init_kernel(uint64_t *words, int nspins, int nrows, int lanes, int segP, int segS,
+                                  uint32_t k0, uint32_t k1, uint32_t row0, int tile)
 {
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= (size_t)nrows * nspins) return;
     const uint32_t row = (uint32_t)(tid % nrows), i = (uint32_t)(tid / nrows);
     uint64_t w = 0;
-    if (tile) {
-        const u32x4 r = philox4x32_10(i, PIQMC_STREAM_INIT << 16, 0u, row0 + row, k0, k1);
-        if (r.x >> 31) w = (lanes == 64) ? ~0ull : ((1ull << lanes) - 1ull);
+    if (tile) {                                      // one bit per (replica, spin), copied to all its slices
+        for (int g = 0; g < segS; g++) {
+            const u32x4 r = philox4x32_10(i, PIQMC_STREAM_INIT << 16, 0u, row0 + row * (uint32_t)segS + g, k0, k1);
+            if (r.x >> 31) w |= seg_ones(segP) << (g * segP);
+        }
     } else {
         for (int l = 0; l < lanes; l++) {
             const u32x4 r = philox4x32_10(i, PIQMC_STREAM_INIT << 16, 0u, (row0 + row) * 64u + l, k0, k1);
@@ -129,18 +134,22 @@ __global__ void state_init_kernel(uint64_t *words, int nspins, int nrows, int la
     words[tid] = w;
 }
 
+// spins: [nrows*segS][nspins] (tile) or [nrows*segS][segP][nspins]; replica row*segS + g -> segment g
 __global__ void pack_spins_kernel(uint64_t *words, const int8_t *spins, int nspins, int nrows,
-                                  int lanes, int tile)
+                                  int segP, int segS, int tile)
 {
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= (size_t)nrows * nspins) return;
     const size_t row = tid % nrows, i = tid / nrows;
     uint64_t w = 0;
-    if (tile) {
-        if (spins[row * nspins + i] < 0) w = (lanes == 64) ? ~0ull : ((1ull << lanes) - 1ull);
-    } else {
-        for (int l = 0; l < lanes; l++)
-            if (spins[(row * lanes + l) * nspins + i] < 0) w |= 1ull << l;
+    for (int g = 0; g < segS; g++) {
+        const size_t rep = row * segS + g;
+        if (tile) {
+            if (spins[rep * nspins + i] < 0) w |= seg_ones(segP) << (g * segP);
+        } else {
+            for (int l = 0; l < segP; l++)
+                if (spins[(rep * segP + l) * nspins + i] < 0) w |= 1ull << (g * segP + l);
+        }
     }
     words[tid] = w;
 }
@@ -149,23 +158,27 @@ __global__ void pack_spins_kernel(uint64_t *words, const int8_t *spins, int nspi
 // spin): the reference's np.tile(spinVector, (P,1)).T start (examples/spinglass32.py:94-96) without
 // a trip through the host.
 __global__ void replicas_to_slices_kernel(const uint64_t *__restrict__ src, uint64_t *__restrict__ dst,
-                                          int nspins, int src_rows, int dst_rows, int lanes)
+                                          int nspins, int src_rows, int dst_rows, int nreplicas, int segP, int segS)
 {
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= (size_t)dst_rows * nspins) return;
-    const size_t r = tid % dst_rows, i = tid / dst_rows;
-    const uint64_t bit = (src[i * src_rows + (r >> 6)] >> (r & 63)) & 1ull;
-    dst[tid] = bit ? ((lanes == 64) ? ~0ull : ((1ull << lanes) - 1ull)) : 0ull;
+    const size_t row = tid % dst_rows, i = tid / dst_rows;
+    uint64_t w = 0;
+    for (int g = 0; g < segS; g++) {
+        const size_t r = row * segS + g;                  // replica; those beyond nreplicas stay +1
+        if (r < (size_t)nreplicas && ((src[i * src_rows + (r >> 6)] >> (r & 63)) & 1ull)) w |= seg_ones(segP) << (g * segP);
+    }
+    dst[tid] = w;
 }
 
 }  // namespace
 
 int launch_replicas_to_slices(piqmc_ctx *c, const uint64_t *d_src, int src_rows, uint64_t *d_dst, int dst_rows,
-                              int lanes)
+                              int nreplicas, int segP, int segS)
 {
     const size_t n = (size_t)dst_rows * c->nspins;
     replicas_to_slices_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(d_src, d_dst, c->nspins, src_rows,
-                                                                                dst_rows, lanes);
+                                                                                dst_rows, nreplicas, segP, segS);
     c->launches++;
     PIQMC_CUDA(cudaGetLastError());
     return PIQMC_OK;
@@ -175,7 +188,8 @@ int launch_state_init(piqmc_ctx *c, uint64_t seed, uint32_t row0, int tile)
 {
     const size_t n = (size_t)c->nrows * c->nspins;
     state_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
-        c->d_words, c->nspins, c->nrows, c->lanes, (uint32_t)seed, (uint32_t)(seed >> 32), row0, tile);
+        c->d_words, c->nspins, c->nrows, c->lanes, c->seg_P, c->seg_S, (uint32_t)seed, (uint32_t)(seed >> 32), row0,
+        tile);
     c->launches++;
     PIQMC_CUDA(cudaGetLastError());
     return PIQMC_OK;
@@ -185,7 +199,7 @@ int launch_pack_spins(piqmc_ctx *c, const int8_t *d_spins, int tile)
 {
     const size_t n = (size_t)c->nrows * c->nspins;
     pack_spins_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_words, d_spins, c->nspins,
-                                                                         c->nrows, c->lanes, tile);
+                                                                         c->nrows, c->seg_P, c->seg_S, tile);
     c->launches++;
     PIQMC_CUDA(cudaGetLastError());
     return PIQMC_OK;

@@ -76,8 +76,10 @@ struct piqmc_ctx {
     int flow_nchunks = 0;
     uint32_t flow_tag = 0;
 
-    // packed state
+    // packed state.  QA states with at most 32 slices may hold several replicas per word: seg_S
+    // segments of seg_P lanes each (lanes = seg_P * seg_S); replica of (row, segment g) = row*seg_S + g
     int nrows = 0, lanes = 0;
+    int seg_P = 0, seg_S = 1;
     uint64_t *d_words = nullptr;    // [N + 1][nrows]  (row fastest); row N stays all-zero
     double *d_energy = nullptr;     // [nrows][lanes]
     void *d_stage = nullptr;        // grow-only staging buffer for host spins
@@ -151,10 +153,10 @@ int launch_sa_det(piqmc_ctx *c, const float *d_temps, int nsched, int mcsteps, i
 int launch_sa_multispin_det(piqmc_ctx *c, const float *d_temps, int nsched, int mcsteps, int ngroups,
                             uint64_t *d_words, const int32_t *d_perms, const double *d_rands);
 
-int launch_state_init(piqmc_ctx *c, uint64_t seed, uint32_t row0, int tile);
+int launch_state_init(piqmc_ctx *c, uint64_t seed, uint32_t row0, int tile);   // row0: first replica id
 int launch_pack_spins(piqmc_ctx *c, const int8_t *d_spins, int tile);
 int launch_replicas_to_slices(piqmc_ctx *c, const uint64_t *d_src, int src_rows, uint64_t *d_dst, int dst_rows,
-                              int lanes);
+                              int nreplicas, int segP, int segS);
 // one colour class (device list `members`) of one sweep; qa != 0: QA rules (jp2 = 2*jperp)
 int launch_colour_sweep(piqmc_ctx *c, int qa, int trotter, const int32_t *members, int nmem, float jp2,
                         float invT, uint64_t seed, uint32_t row0, uint32_t sweep);

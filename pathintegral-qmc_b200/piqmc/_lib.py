@@ -58,7 +58,9 @@ SIGNATURES = {
     "piqmc_sa_multispin_det": (c_int, [c_void, c_void, c_int, c_int, c_int, c_void, c_void, c_void]),
     "piqmc_jperp": (c_f, [c_d, c_int, c_f]),
     "piqmc_state_alloc": (c_int, [c_void, c_int, c_int]),
+    "piqmc_state_alloc_packed": (c_int, [c_void, c_int, c_int, c_int]),
     "piqmc_state_replicas_to_slices": (c_int, [c_void, c_int, c_int]),
+    "piqmc_state_replicas_to_slices_packed": (c_int, [c_void, c_int, c_int, c_int]),
     "piqmc_state_init_random": (c_int, [c_void, c_u64, c_u32, c_int]),
     "piqmc_state_upload_spins": (c_int, [c_void, c_void, c_int]),
     "piqmc_state_upload_words": (c_int, [c_void, c_void]),

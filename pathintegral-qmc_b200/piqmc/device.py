@@ -59,6 +59,9 @@ class Device:
         self.ncolors = 0
         self.nrows = 0
         self.lanes = 0
+        self.slices = 0          # slices per replica (== lanes unless several replicas share a word)
+        self.per_word = 1        # replicas per word
+        self.variant = 0
         self._graph_key = None
 
     def close(self):
@@ -87,6 +90,7 @@ class Device:
 
     def set_variant(self, variant):
         check(lib.piqmc_set_variant(self._h, int(variant)))
+        self.variant = int(variant)
 
     def set_global_moves(self, enable):
         """World-line (all-slices) moves after the local moves of every spin (QA, maxnb <= 4)."""
@@ -217,24 +221,46 @@ class Device:
         return u, u.shape[1]
 
     # ------------------------------------------------------------------ packed state
-    def state_alloc(self, nrows, lanes):
-        check(lib.piqmc_state_alloc(self._h, int(nrows), int(lanes)))
-        self.nrows, self.lanes = int(nrows), int(lanes)
+    def state_alloc(self, nrows, lanes, per_word=1):
+        """nrows words per spin of `lanes` lanes.  per_word > 1 (QA, lanes <= 32 slices, a multiple
+        of 4): every word holds per_word replicas of `lanes` slices each, replica row*per_word + g in
+        bits [g*lanes, (g+1)*lanes); the host-facing methods below then count in replicas."""
+        check(lib.piqmc_state_alloc_packed(self._h, int(nrows), int(lanes), int(per_word)))
+        self.nrows, self.slices, self.per_word = int(nrows), int(lanes), int(per_word)
+        self.lanes = self.slices * self.per_word
 
-    def state_replicas_to_slices(self, nreplicas, slices):
-        """SA state (64 replicas per word) -> QA state (row per replica, all slices = its spin),
-        on the device."""
-        check(lib.piqmc_state_replicas_to_slices(self._h, int(nreplicas), int(slices)))
-        self.nrows, self.lanes = int(nreplicas), int(slices)
+    def state_replicas_to_slices(self, nreplicas, slices, per_word=1):
+        """SA state (64 replicas per word) -> QA state (all slices of a replica = its spin), on the
+        device."""
+        check(lib.piqmc_state_replicas_to_slices_packed(self._h, int(nreplicas), int(slices), int(per_word)))
+        self.per_word, self.slices = int(per_word), int(slices)
+        self.nrows = (int(nreplicas) + self.per_word - 1) // self.per_word
+        self.lanes = self.slices * self.per_word
+
+    @property
+    def nreplicas_held(self):
+        """replicas a QA state holds (rows x replicas per word)"""
+        return self.nrows * self.per_word
+
+    def _unpack_replicas(self, raw):
+        """packed words [nspins, nrows] -> [nrows*per_word, nspins] with bit k = slice k"""
+        if self.per_word == 1:
+            return raw.T
+        ones = np.uint64((1 << self.slices) - 1)
+        out = np.empty((self.nrows, self.per_word, self.nspins), dtype=np.uint64)
+        for g in range(self.per_word):
+            out[:, g, :] = ((raw >> np.uint64(g * self.slices)) & ones).T
+        return out.reshape(self.nrows * self.per_word, self.nspins)
 
     def state_init_random(self, seed, row0=0, tile=True):
         check(lib.piqmc_state_init_random(self._h, int(seed), int(row0), 1 if tile else 0))
 
     def state_upload_spins(self, spins, tile=True):
-        """tile: spins int8[nrows,N] copied to every lane; else int8[nrows,lanes,N]."""
+        """tile: spins int8[R,N] copied to every slice; else int8[R,slices,N]; R = nrows*per_word."""
         if not (isinstance(spins, np.ndarray) and spins.dtype == np.int8 and spins.flags.c_contiguous):
             spins = np.ascontiguousarray(spins, dtype=np.int8)
-        want = (self.nrows, self.nspins) if tile else (self.nrows, self.lanes, self.nspins)
+        R = self.nrows * self.per_word
+        want = (R, self.nspins) if tile else (R, self.slices, self.nspins)
         if spins.shape != want:
             raise ValueError("spins must have shape %s" % (want,))
         check(lib.piqmc_state_upload_spins(self._h, _ptr(spins), 1 if tile else 0))
@@ -256,12 +282,12 @@ class Device:
         elif out.dtype != np.uint64 or not out.flags.c_contiguous or out.shape != (self.nspins, self.nrows):
             raise ValueError("out must be C-contiguous uint64[nspins, nrows]")
         check(lib.piqmc_state_download_words(self._h, _ptr(out)))
-        return out.T
+        return self._unpack_replicas(out)
 
     def state_download_spins(self):
         """int8[nrows, lanes, N] of +-1 (host-side unpack of the packed words)."""
         w = self.state_download_words()
-        lanes = np.arange(self.lanes, dtype=np.uint64)
+        lanes = np.arange(self.slices or self.lanes, dtype=np.uint64)
         bits = (w[:, None, :] >> lanes[None, :, None]) & np.uint64(1)
         return (1 - 2 * bits.astype(np.int8)).astype(np.int8)
 
@@ -270,7 +296,8 @@ class Device:
         return DeviceArray(lib.piqmc_state_devptr(self._h), (self.nspins, self.nrows), "<u8", self)
 
     def energy_device_array(self):
-        return DeviceArray(lib.piqmc_energy_devptr(self._h), (self.nrows, self.lanes), "<f8", self)
+        return DeviceArray(lib.piqmc_energy_devptr(self._h),
+                           (self.nrows * self.per_word, self.lanes // self.per_word), "<f8", self)
 
     # ------------------------------------------------------------------ production sweeps
     def _orders(self, orders, nsweeps):
@@ -312,7 +339,7 @@ class Device:
             return None
         out = np.empty((self.nrows, self.lanes), dtype=np.float64)
         check(lib.piqmc_energy(self._h, _ptr(out)))
-        return out
+        return out.reshape(self.nrows * self.per_word, self.lanes // self.per_word)
 
     def results(self, words_out=None):
         """(energies float64[nrows, lanes], words uint64 view [nrows, nspins]) in one call; the
@@ -324,7 +351,8 @@ class Device:
               or words_out.shape != (self.nspins, self.nrows)):
             raise ValueError("words_out must be C-contiguous uint64[nspins, nrows]")
         check(lib.piqmc_results(self._h, _ptr(en), _ptr(words_out)))
-        return en, words_out.T
+        return (en.reshape(self.nrows * self.per_word, self.lanes // self.per_word),
+                self._unpack_replicas(words_out))
 
     def energy_coo(self, nspins, row, col, val, spins):
         row = np.ascontiguousarray(row, dtype=np.int32)

@@ -125,7 +125,8 @@ def QuantumAnneal_parallel(sched, mcsteps, slices, temp, nspins, confs, nbs, nth
 
 def QuantumAnnealReplicas(sched, mcsteps, slices, temp, nspins, spins0, nbs, seed, order="natural",
                           color=None, replica0=0, trotter="reference", device=None, energies=True,
-                          tile=True, nreplicas=None, download=True, words_out=None, global_moves=False):
+                          tile=True, nreplicas=None, download=True, words_out=None, global_moves=False,
+                          per_word="auto"):
     """Production PIQMC: R replicas x `slices` Trotter slices x nspins, one uint64 word per
     (replica, spin) holding all slices, colour-class Metropolis sweeps with Philox4x32-10 keyed by
     (seed; spin, slice, sweep, replica0 + r), J_perp recomputed per schedule step.
@@ -147,7 +148,11 @@ def QuantumAnnealReplicas(sched, mcsteps, slices, temp, nspins, spins0, nbs, see
             np.tile(spinVector, (P,1)).T start), or int8[R, slices, nspins] (tile=False), or None
             for a Philox-generated random start (give nreplicas).
     words_out: optional C-contiguous uint64[nspins, R] host buffer (e.g. device.pinned_empty) that
-            receives the packed state in device layout.
+            receives the packed state in device layout (one replica per word only).
+    per_word: replicas per 64-bit word.  "auto": floor(64/slices) when slices <= 32 is a multiple of 4,
+            the Trotter mode is the reference's, there are no world-line moves and the table kernel
+            applies (maxnb <= 4) -- e.g. 3 replicas per word at P = 20; results are the same replica
+            by replica as with one replica per word.
     Returns dict(words=uint64[R,nspins] (bit k <-> slice k, set <-> spin -1; a transposed view of
                  the spin-major buffer), energies=float64[R,slices] ClassicalIsingEnergy per slice)."""
     sched = np.ascontiguousarray(sched, dtype=np.float64)
@@ -166,15 +171,28 @@ def QuantumAnnealReplicas(sched, mcsteps, slices, temp, nspins, spins0, nbs, see
         raise ValueError("nspins=%d but nbs describes %d spins" % (nspins, d.nspins))
     resident = isinstance(spins0, str) and spins0 == "resident"
     R = int(nreplicas) if (spins0 is None or resident) else int(np.asarray(spins0).shape[0])
+    S = 1
+    if per_word == "auto":
+        if (slices <= 32 and slices % 4 == 0 and TROTTER[trotter] == 0 and not global_moves
+                and d.maxnb <= 4 and d.variant != 1):
+            S = 64 // slices
+            while S > 1 and (R + S - 1) // S < 32 and d.variant != 2:   # the table kernel wants >= 32 rows
+                S -= 1
+    else:
+        S = int(per_word)
+    rows = (R + S - 1) // S
     if not resident:
-        d.state_alloc(R, slices)
+        d.state_alloc(rows, slices, S)
     t.append(time.perf_counter())
     if resident:
-        d.state_replicas_to_slices(R, slices)
+        d.state_replicas_to_slices(R, slices, S)
     elif spins0 is None:
         d.state_init_random(seed, replica0, tile=True)
     else:
-        d.state_upload_spins(spins0, tile=tile)
+        sp = np.asarray(spins0, dtype=np.int8)
+        if rows * S != R:                               # pad the last word with +1 replicas (discarded below)
+            sp = np.concatenate([sp, np.ones((rows * S - R,) + sp.shape[1:], dtype=np.int8)])
+        d.state_upload_spins(sp, tile=tile)
     t.append(time.perf_counter())
     d.set_global_moves(global_moves)
     try:
@@ -185,16 +203,21 @@ def QuantumAnnealReplicas(sched, mcsteps, slices, temp, nspins, spins0, nbs, see
     t.append(time.perf_counter())
     out = {"energies": None, "words": None}
     if energies and download:
-        out["energies"], out["words"] = d.results(words_out)
+        out["energies"], out["words"] = d.results(words_out if S == 1 else None)
         t.append(time.perf_counter())
     else:
         if energies:
             out["energies"] = d.energy(download=download)
         t.append(time.perf_counter())
         if download:
-            out["words"] = d.state_download_words(out=words_out)
+            out["words"] = d.state_download_words(out=words_out if S == 1 else None)
         else:
             d.synchronize()
     t.append(time.perf_counter())
+    if rows * S != R:                                   # drop the padding replicas of the last word
+        for key in ("energies", "words"):
+            if isinstance(out[key], np.ndarray):
+                out[key] = out[key][:R]
+    out["per_word"] = S
     out["seconds"] = dict(zip(("graph+alloc", "upload", "sweeps", "energy", "download"), np.diff(t).tolist()))
     return out

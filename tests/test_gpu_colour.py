@@ -179,8 +179,8 @@ def test_resident_handover_sa_to_qa_and_results(dev, R, P):
     assert np.array_equal(res["words"], host["words"])
     assert np.array_equal(res["energies"], host["energies"])
     # the separate calls agree with the combined one
-    assert np.array_equal(dev.energy(), res["energies"])
-    assert np.array_equal(dev.state_download_words(), res["words"])
+    assert np.array_equal(dev.energy()[:R], res["energies"])          # [:R]: a packed state pads its last word
+    assert np.array_equal(dev.state_download_words()[:R], res["words"])
     # and with the CPU statement of the whole chain
     want = pre["spins"].copy()
     ref = np.repeat(want[:, :, None], P, axis=2).copy()
@@ -489,3 +489,35 @@ def test_config5_full_size_properties(dev):
     start = qmc.QuantumAnnealReplicas(sched[:0], 1, P, 0.01, n, None, nbs, 2024, color=color, nreplicas=64,
                                       device=dev)
     assert e_full.mean() < start["energies"].mean() - 0.5 * n
+
+
+# ------------------------------------------------------------------- several replicas per word
+@pytest.mark.parametrize("P,R,T", [(20, 100, 0.01), (20, 97, 0.3), (16, 130, 0.05), (8, 300, 0.5), (4, 520, 0.2),
+                                   (32, 70, 0.3), (12, 161, 1.0)])
+def test_replicas_per_word_bit_exact(dev, P, R, T):
+    """P <= 32 slices: floor(64/P) replicas share a word (3 at P = 20).  The result is, replica by
+    replica, the one of the one-replica-per-word layout and of the CPU statement -- same Philox keys
+    -- for cold and hot (many draws) anneals, replica counts that do not fill the last word, a
+    non-zero first replica id, and both ways of starting (Philox start, uploaded spins)."""
+    import piqmc.qmc as qmc
+    nbs, idx, J32, color = _torus(8, 21)
+    n = 64
+    sched = np.linspace(1.5, 1e-8, 7)
+    seed, r0 = 77 + P, 5
+    init = O.colour_init_spins(seed, r0, R, n)
+    want = np.repeat(init[:, :, None], P, axis=2).copy()
+    O.qa_colour(sched, 2, P, T, idx, J32, color, want, seed, replica0=r0)
+    dev.set_variant(2)
+    try:
+        one = qmc.QuantumAnnealReplicas(sched, 2, P, T, n, None, nbs, seed, color=color, nreplicas=R, replica0=r0,
+                                        device=dev, per_word=1)
+        many = qmc.QuantumAnnealReplicas(sched, 2, P, T, n, None, nbs, seed, color=color, nreplicas=R, replica0=r0,
+                                         device=dev)
+        up = qmc.QuantumAnnealReplicas(sched, 2, P, T, n, init, nbs, seed, color=color, replica0=r0, device=dev)
+    finally:
+        dev.set_variant(0)
+    assert one["per_word"] == 1 and many["per_word"] == 64 // P and up["per_word"] == 64 // P
+    got = np.transpose(tools.UnpackWords(many["words"], P), (0, 2, 1))
+    assert np.array_equal(got, want)
+    assert np.array_equal(many["words"], one["words"]) and np.array_equal(up["words"], one["words"])
+    assert np.array_equal(many["energies"], one["energies"]) and np.array_equal(up["energies"], one["energies"])
