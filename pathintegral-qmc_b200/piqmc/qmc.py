@@ -176,7 +176,13 @@ def QuantumAnnealReplicas(sched, mcsteps, slices, temp, nspins, spins0, nbs, see
         if (slices <= 32 and slices % 4 == 0 and TROTTER[trotter] == 0 and not global_moves
                 and d.maxnb <= 4 and d.variant != 1):
             S = 64 // slices
-            while S > 1 and (R + S - 1) // S < 32 and d.variant != 2:   # the table kernel wants >= 32 rows
+            # Packing divides the rows by S.  That pays when a wavefront step (one colour class, all
+            # rows) still offers several times the words the GPU holds in flight (~170k); with many
+            # small classes (natural order on a small lattice) the sweep is bound by the dependency
+            # chain and fewer rows only make it worse (measured: tools/bench_configs.py).
+            nclasses = (int(np.max(color)) + 1) if orders is None else 16
+            per_step = max(1, int(nspins) // nclasses)
+            while S > 1 and d.variant != 2 and ((R + S - 1) // S < 32 or per_step * ((R + S - 1) // S) < 350000):
                 S -= 1
     else:
         S = int(per_word)

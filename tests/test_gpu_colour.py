@@ -174,8 +174,10 @@ def test_resident_handover_sa_to_qa_and_results(dev, R, P):
                                      device=dev)
     assert np.array_equal(res2["words"], host2["words"])
     sa.AnnealReplicas(ssched, 1, None, nbs, 11, color=color, nreplicas=R, device=dev, download=False)
+    # (at P = 20 the hand-over also changes the layout: 3 replicas per word, the last word padded)
     res = qmc.QuantumAnnealReplicas(qsched, 1, P, 0.01, 64, "resident", nbs, 12, color=color, nreplicas=R,
-                                    device=dev)
+                                    device=dev, per_word=3 if P == 20 else 1)
+    assert res["per_word"] == (3 if P == 20 else 1) and host["per_word"] == 1
     assert np.array_equal(res["words"], host["words"])
     assert np.array_equal(res["energies"], host["energies"])
     # the separate calls agree with the combined one
