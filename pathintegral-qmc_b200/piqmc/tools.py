@@ -24,7 +24,7 @@ def spins2bits(vec):
     return [0 if k == 1 else 1 for k in vec]
 
 
-def GenerateNeighbors(nspins, J, maxnb, savepath=None):
+def GenerateNeighbors(nspins, J, maxnb, savepath=None, colouring=None):
     """Neighbour table of the Ising graph @J: float64[nspins, maxnb, 2] with
     [:, :, 0] = neighbour index and [:, :, 1] = coupling; a diagonal entry J[i,i] (local field)
     appears as a self-neighbour of i; unused rows stay [0, 0].
@@ -33,7 +33,11 @@ def GenerateNeighbors(nspins, J, maxnb, savepath=None):
     (a, b) with a == i (-> neighbour b) or b == i (-> neighbour a).  The reference rescans all keys
     for every spin (O(N*nnz)); this walks the keys once and appends to both endpoint rows, which
     yields the same rows in the same order.  A spin with more than @maxnb entries raises
-    IndexError, as the reference's bounds-checked buffer write does."""
+    IndexError, as the reference's bounds-checked buffer write does.
+
+    @colouring (not in the reference): None returns the table alone, like the reference;
+    "natural" / "checkerboard" / an int order array returns (table, colour classes) with the
+    classes of ColourGraph(table, colouring) -- what the production kernels sweep by."""
     nspins = int(nspins)
     maxnb = int(maxnb)
     nbs = np.zeros((nspins, maxnb, 2))
@@ -54,6 +58,8 @@ def GenerateNeighbors(nspins, J, maxnb, savepath=None):
             fill[ispin] = k + 1
     if savepath is not None:
         np.save(savepath, nbs)
+    if colouring is not None:
+        return nbs, ColourGraph(nbs, colouring)
     return nbs
 
 

@@ -142,3 +142,17 @@ def test_lattice_generators_match_reference():
         assert np.array_equal(np.array(list(J.keys()), dtype=np.int64).reshape(-1, 2), vec["keys%d" % k]), c
         assert rng.randint(1 << 30) == int(vec["next%d" % k][0]), c
         assert (J - sps.triu(J)).nnz == 0
+
+
+def test_generateneighbors_with_colouring(golden):
+    """GenerateNeighbors(..., colouring=...) hands back the table the reference returns plus the
+    colour classes the production kernels sweep by (a proper colouring either way)."""
+    J = tools.IsingFromTriples(golden["inst"]["inst_inst_0_32x32"], 1024)
+    nbs = tools.GenerateNeighbors(1024, J, 4)
+    for mode, nclasses in (("checkerboard", 2), ("natural", 63)):
+        nbs2, color = tools.GenerateNeighbors(1024, J, 4, colouring=mode)
+        assert np.array_equal(nbs, nbs2) and color.shape == (1024,) and color.max() + 1 == nclasses
+        for i in range(1024):
+            for j, v in nbs[i]:
+                if v != 0.0 and int(j) != i:
+                    assert color[int(j)] != color[i]
