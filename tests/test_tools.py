@@ -156,3 +156,42 @@ def test_generateneighbors_with_colouring(golden):
             for j, v in nbs[i]:
                 if v != 0.0 and int(j) != i:
                     assert color[int(j)] != color[i]
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_level_colouring_equals_sequential_sweep_on_random_graphs(seed):
+    """The claim the production path rests on: sweeping the dependency levels
+    of a visiting order, a whole level at once, IS the sequential sweep in that order.  Checked on
+    the CPU statement of the colour semantics, on random sparse graphs with fields, random orders,
+    QA (both Trotter modes) and SA, hot enough that most attempts draw a uniform."""
+    from oracle import oracle as O
+    rng = np.random.RandomState(1000 + seed)
+    n, maxnb = 24 + 3 * seed, 5
+    J = sps.dok_matrix((n, n))
+    deg = np.zeros(n, dtype=int)
+    for _ in range(3 * n):
+        a, b = rng.randint(n, size=2)
+        if a != b and (min(a, b), max(a, b)) not in J and deg[a] < maxnb - 1 and deg[b] < maxnb - 1:
+            J[min(a, b), max(a, b)] = rng.uniform(-2, 2)
+            deg[a] += 1
+            deg[b] += 1
+    for i in rng.choice(n, n // 3, replace=False):
+        J[i, i] = rng.uniform(-1, 1)
+    nbs = tools.GenerateNeighbors(n, J, maxnb)
+    idx, J32 = O.nbs_to_ell(nbs)
+    order = rng.permutation(n).astype(np.int32)
+    levels = tools.OrderLevels(nbs, order)
+    assert np.array_equal(levels, tools.ColourGraph(nbs, order))
+    nsweeps, P, R = 4, 6, 3
+    sched = np.linspace(1.5, 0.2, nsweeps)
+    init = (2 * rng.randint(2, size=(R, n)) - 1).astype(np.int8)
+    for trotter in (0, 1):
+        a = np.repeat(init[:, :, None], P, axis=2).copy()
+        b = a.copy()
+        O.qa_colour(sched, 1, P, 0.7, idx, J32, levels, a, 5, trotter=trotter)
+        O.qa_colour(sched, 1, P, 0.7, idx, J32, levels, b, 5, trotter=trotter, orders=np.tile(order, (nsweeps, 1)))
+        assert np.array_equal(a, b)
+    a, b = init.copy(), init.copy()
+    O.sa_colour(np.linspace(2.0, 0.3, nsweeps), 1, idx, J32, levels, a, 9)
+    O.sa_colour(np.linspace(2.0, 0.3, nsweeps), 1, idx, J32, levels, b, 9, orders=np.tile(order, (nsweeps, 1)))
+    assert np.array_equal(a, b)
