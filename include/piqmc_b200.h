@@ -192,8 +192,26 @@ int piqmc_sa_colour(piqmc_handle h, const double *sched, int nsched, int mcsteps
  * default; needs maxnb <= 4.  Specification: oracle/piqmc_oracle.c, oracle_qa_colour. */
 int piqmc_set_global_moves(piqmc_handle h, int enable);
 /* kernel variant selection for piqmc_qa_colour / piqmc_sa_colour: 0 = auto, 1 = generic,
- * 2 = table-lookup fast path (falls back to generic when the graph does not qualify) */
+ * 2 = dataflow kernel (one unit per (sweep, spin, row chunk); falls back to generic when the graph
+ * does not qualify), 3 = chain pipeline (natural-order colourings with maxnb <= 4; falls back to 2) */
 int piqmc_set_variant(piqmc_handle h, int variant);
+/* Chain pipeline (the natural-order sweep of qmc.pyx:320-357 cut into contiguous chains of chain_len
+ * spins, one warp per chain and 32 rows): chain_len = 0 lets the library choose (a lattice row);
+ * > 0 forces that length and the pipeline (testing, tuning).  piqmc_chain_info reports the plan of
+ * the current graph + colouring: chain_len = 0 when there is none (colouring is not the natural
+ * order's, or maxnb > 4); period = modelled pipeline steps per sweep; selected = 1 when a static-colouring run
+ * (reference Trotter neighbours, no world-line moves) would take the pipeline under the current variant. */
+int piqmc_set_chain(piqmc_handle h, int chain_len);
+int piqmc_chain_info(piqmc_handle h, int *chain_len, int *nchains, double *period, int *selected);
+/* The plan itself, on the host (no device needed): for the natural-order sweep of the ELL table
+ * (idx, J) cut into chains of chain_len spins (0 = choose), kinds[i*4 + k] is where sorted table
+ * column k of spin i (columns sorted by |J| descending, stable) gets its neighbour word from
+ * (0 none, 1 the word just written, 2 the next own word, 3/4 hand-over ring of the preceding chain
+ * for this / the previous sweep, 5 state word of the own chain, 6/7 progress-guarded state word of
+ * another chain for this / the previous sweep), loc[i*4 + k] = (chain << 16) | position of that
+ * neighbour.  Returns the chain length (0: no plan, < 0: error). */
+int piqmc_chain_plan(int nspins, int maxnb, const int32_t *idx, const double *J, int chain_len,
+                     uint8_t *kinds, uint32_t *loc, double *period);
 
 /* sa.ClassicalIsingEnergy (piqmc/sa.pyx:25-44) of every (row, lane) of the resident state,
  * float64: energies[row*lanes + lane].  energies may be NULL (result stays on the device). */

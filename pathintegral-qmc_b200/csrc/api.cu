@@ -48,6 +48,8 @@ void free_graph(piqmc_ctx *c)
     free_dev(c->d_level);
     free_dev(c->d_recs);
     free_dev(c->d_done);
+    free_dev(c->d_cstat);
+    c->chain_ok = c->chain_C = c->chain_n = 0;
     c->flow_nchunks = 0;
     c->color_off.clear();
     c->nspins = c->maxnb = c->ncolors = 0;
@@ -157,6 +159,183 @@ static void build_unit_recs(const piqmc_ctx *h, const int32_t *level, const int3
     }
 }
 
+
+// ---- chain plan (chain_kernels.cu) -------------------------------------------------------------
+// The natural-order sweep cut into contiguous chains of C spins.  Slot kinds of spin i (sorted
+// columns, as in build_unit_recs): see PIQMC_K_* in common.cuh.
+struct GraphView {            // host view of an ELL table (float32 couplings, live = coupled to another spin)
+    int nspins, maxnb;
+    const int32_t *h_idx;
+    const float *h_J32;
+    const uint8_t *h_live;
+};
+
+static void build_chain_stat(const GraphView *h, int C, std::vector<PiqmcChainStat> &out)
+{
+    const int N = h->nspins, mb = h->maxnb < 4 ? h->maxnb : 4;
+    const int nchains = (N + C - 1) / C;
+    out.assign(N, PiqmcChainStat());
+    for (int i = 0; i < N; i++) {
+        int32_t nb[4];
+        float J[4];
+        uint8_t livef[4];
+        for (int n = 0; n < 4; n++) {
+            nb[n] = -1;
+            J[n] = 0.0f;
+            livef[n] = 0;
+            if (n < mb) {
+                const size_t e = (size_t)i * h->maxnb + n;
+                J[n] = h->h_J32[e];
+                if (h->h_live[e]) {
+                    nb[n] = h->h_idx[e];
+                    livef[n] = 1;
+                }
+            }
+        }
+        int col[4] = {0, 1, 2, 3};
+        std::stable_sort(col, col + 4, [&](int a, int b) { return fabsf(J[a]) > fabsf(J[b]); });
+        PiqmcChainStat &r = out[i];
+        const int ci = i / C, pi = i % C;
+        const int pred = ci == 0 ? nchains - 1 : ci - 1;
+        uint32_t kinds = 0, pad = 0;
+        float Js[4];
+        for (int z = 0; z < 4; z++) {
+            const int n = col[z];
+            Js[z] = J[n];
+            pad |= (uint32_t)n << (2 * z);
+            if (J[n] < 0.0f) pad |= 1u << (8 + z);
+            uint32_t kind = PIQMC_K_ZERO;
+            r.loc[z] = 0;
+            if (livef[n]) {
+                const int j = nb[n], cj = j / C, pj = j % C;
+                if (cj == ci) kind = (j == i - 1) ? PIQMC_K_PREV : (j == i + 1 ? PIQMC_K_NEXT : PIQMC_K_MEM_SELF);
+                else if (pj == pi && cj == pred) kind = j < i ? PIQMC_K_LL_CUR : PIQMC_K_LL_OLD;
+                else kind = j < i ? PIQMC_K_MEM_CUR : PIQMC_K_MEM_OLD;
+                r.loc[z] = ((uint32_t)cj << 16) | (uint32_t)pj;
+            }
+            kinds |= kind << (8 * z);
+        }
+        r.kinds = kinds;
+        r.pad = pad;
+        r.J01[0] = Js[0];
+        r.J01[1] = Js[1];
+        r.J23[0] = Js[2];
+        r.J23[1] = Js[3];
+        r.spare[0] = r.spare[1] = 0;
+    }
+}
+
+// Modelled period (in steps of one warp) of the chain pipeline in steady state: event times of three
+// sweeps with unit step cost, a hand-over costing LL and a progress-guarded state word costing MEM
+// (publication every 8 steps + an L2 round trip).  c = C for a perfect pipeline.
+static double chain_model_period(const GraphView *h, const std::vector<PiqmcChainStat> &st, int C)
+{
+    const int N = h->nspins;
+    const double LL = 0.3, MEM = 6.0;
+    std::vector<double> prev(N, 0.0), cur(N, 0.0);
+    double period = 0.0;
+    for (int s = 0; s < 3; s++) {
+        for (int i = 0; i < N; i++) {
+            double t = (i % C) ? cur[i - 1] : (s ? prev[std::min(N - 1, i + C - 1 - (i % C))] : 0.0);
+            for (int z = 0; z < 4; z++) {
+                const uint32_t kind = (st[i].kinds >> (8 * z)) & 0xFFu;
+                if (kind < PIQMC_K_LL_CUR) continue;
+                const int j = (int)(st[i].loc[z] >> 16) * C + (int)(st[i].loc[z] & 0xFFFFu);
+                double d = 0.0;
+                switch (kind) {
+                case PIQMC_K_LL_CUR: d = cur[j] + LL; break;
+                case PIQMC_K_LL_OLD: d = s ? prev[j] + LL : 0.0; break;
+                case PIQMC_K_MEM_CUR: d = cur[j] + MEM; break;
+                case PIQMC_K_MEM_OLD: d = s ? prev[j] + MEM : 0.0; break;
+                default: break;
+                }
+                if (d > t) t = d;
+            }
+            cur[i] = t + 1.0;
+        }
+        if (s == 2)
+            for (int i = 0; i < N; i++) period = std::max(period, cur[i] - prev[i]);
+        prev.swap(cur);
+    }
+    return period;
+}
+
+// Choose the chain length (or take the forced one) and upload the static records.  Candidates: the
+// most frequent index distances of coupled pairs (a lattice row), and one chain for everything.
+static int choose_chain(const GraphView *h, int force_C, std::vector<PiqmcChainStat> &best, double &best_period)
+{
+    const int N = h->nspins;
+    std::vector<int> cand;
+    if (force_C > 0) cand.push_back(std::min(force_C, N));
+    else {
+        std::vector<std::pair<int, int>> hist;                 // (distance, count)
+        {
+            std::vector<int> d;
+            for (int i = 0; i < N; i++)
+                for (int n = 0; n < h->maxnb; n++) {
+                    const size_t e = (size_t)i * h->maxnb + n;
+                    if (h->h_live[e] && h->h_idx[e] > i + 1) d.push_back(h->h_idx[e] - i);
+                }
+            std::sort(d.begin(), d.end());
+            for (size_t k = 0; k < d.size();) {
+                size_t m = k;
+                while (m < d.size() && d[m] == d[k]) m++;
+                hist.push_back({d[k], (int)(m - k)});
+                k = m;
+            }
+            std::sort(hist.begin(), hist.end(), [](const std::pair<int, int> &a, const std::pair<int, int> &b) {
+                return a.second != b.second ? a.second > b.second : a.first < b.first;
+            });
+        }
+        for (size_t k = 0; k < hist.size() && cand.size() < 3; k++) cand.push_back(hist[k].first);
+        cand.push_back(N);
+    }
+    best_period = 0.0;
+    int best_C = 0;
+    for (int C : cand) {
+        if (C < 4 || C > 65535 || (N + C - 1) / C > 65535) continue;
+        if (N - ((N + C - 1) / C - 1) * C < 2 && (N + C - 1) / C > 1) continue;      // a last chain of one spin: the
+                                                                                     // kernel requests own words 2 steps ahead
+        std::vector<PiqmcChainStat> st;
+        build_chain_stat(h, C, st);
+        const double period = chain_model_period(h, st, C);
+        if (best_C == 0 || period < best_period) {
+            best_period = period;
+            best_C = C;
+            best.swap(st);
+        }
+    }
+    return best_C;
+}
+
+static int build_chain_plan(piqmc_ctx *h)
+{
+    h->chain_C = h->chain_n = 0;
+    if (!h->chain_ok) return PIQMC_OK;
+    const int N = h->nspins;
+    const GraphView gv = {N, h->maxnb, h->h_idx.data(), h->h_J32.data(), h->h_live.data()};
+    std::vector<PiqmcChainStat> best;
+    double best_period = 0.0;
+    const int best_C = choose_chain(&gv, h->chain_force_C, best, best_period);
+    if (best_C == 0) return PIQMC_OK;
+    if (!h->d_cstat) PIQMC_CUDA(cudaMalloc(&h->d_cstat, (size_t)N * sizeof(PiqmcChainStat)));
+    PIQMC_CUDA(cudaMemcpy(h->d_cstat, best.data(), (size_t)N * sizeof(PiqmcChainStat), cudaMemcpyHostToDevice));
+    h->chain_C = best_C;
+    h->chain_n = (N + best_C - 1) / best_C;
+    h->chain_period = best_period;
+    return PIQMC_OK;
+}
+
+// Which kernel runs a static colouring: the chain pipeline when the colouring is the natural order's
+// and its modelled critical path (steps of ~0.6 us) beats the dataflow kernel's (levels of ~3.6 us).
+static bool chain_selected(const piqmc_ctx *h, int qa, int trotter)
+{
+    if (h->chain_C < 4 || h->variant == 1 || h->variant == 2 || h->global_moves || (qa && trotter)) return false;
+    if (h->variant == 3 || h->chain_force_C > 0) return true;
+    if (const char *e = getenv("PIQMC_CHAIN")) return atoi(e) != 0;
+    return h->chain_period <= 6.0 * (double)h->ncolors;
+}
+
 static int apply_colouring(piqmc_ctx *h, int ncolors, const int32_t *color, bool validate)
 {
     if (validate) {
@@ -202,7 +381,17 @@ static int apply_colouring(piqmc_ctx *h, int ncolors, const int32_t *color, bool
     }
     h->flow_extra = (ncolors + D - 1) / D - 1;
     h->ncolors = ncolors;
-    return PIQMC_OK;
+    // the chain kernel runs the natural order: usable when that order has this level colouring
+    h->chain_ok = h->maxnb <= 4 ? 1 : 0;
+    for (int i = 0; i < h->nspins && h->chain_ok; i++)
+        for (int n = 0; n < h->maxnb; n++) {
+            const size_t e = (size_t)i * h->maxnb + n;
+            if (h->h_live[e] && h->h_idx[e] > i && color[h->h_idx[e]] <= color[i]) {
+                h->chain_ok = 0;
+                break;
+            }
+        }
+    return build_chain_plan(h);
 }
 
 // level[i] = 1 + max(level of coupled neighbours visited earlier); returns the number of levels
@@ -250,7 +439,9 @@ static int run_colour_sweeps(piqmc_ctx *h, int qa, int trotter, int nsched, int 
     const int N = h->nspins;
     const size_t nsweeps = (size_t)nsched * mcsteps;
     if (nsweeps == 0) return PIQMC_OK;
-    const bool fast = piqmc_fast_ok(h, qa, trotter);
+    // static colourings with many levels and a small level gap (a path graph in natural order) would need
+    // more units than one grid holds: those run class by class (or through the chain pipeline below)
+    const bool fast = piqmc_fast_ok(h, qa, trotter) && (orders || launch_fast_fits(h, h->flow_extra));
     if (!orders) PIQMC_REQUIRE(h->ncolors > 0, PIQMC_ENOGRAPH, "graph has no colouring");
     else TRY(check_orders(N, nsweeps, orders));
 
@@ -269,13 +460,15 @@ static int run_colour_sweeps(piqmc_ctx *h, int qa, int trotter, int nsched, int 
         PIQMC_CUDA(cudaStreamSynchronize(h->stream));     // a, b are about to go out of scope
     }
 
+    if (!orders && chain_selected(h, qa, trotter))
+        return launch_chain_sweeps(h, qa, nsched, mcsteps, jp2.data(), invT.data(), seed, row0, sweep0);
     if (!orders) {
         if (fast) {
             TRY(launch_fast_sweeps(h, qa, trotter, (int)nsweeps, h->d_recs, h->flow_extra, 0, d_jp2.p, d_invT.p, seed,
                                    row0, sweep0));
             // the per-sweep parameter arrays must outlive the launch
             PIQMC_CUDA(cudaStreamSynchronize(h->stream));
-            return PIQMC_OK;
+            return piqmc_check_watchdog(h, "dataflow sweeps");
         }
         uint32_t sweep = sweep0;
         for (int f = 0; f < nsched; f++)
@@ -325,6 +518,7 @@ static int run_colour_sweeps(piqmc_ctx *h, int qa, int trotter, int nsched, int 
             }
         }
         PIQMC_CUDA(cudaStreamSynchronize(h->stream));     // lists are reused or freed next
+        if (fast) TRY(piqmc_check_watchdog(h, "dataflow sweeps"));
     }
     return PIQMC_OK;
 }
@@ -384,6 +578,10 @@ int piqmc_destroy(piqmc_handle h)
     free_dev(h->d_epart);
     free_dev(h->d_ticket);
     free_dev(h->d_stage);
+    free_dev(h->d_err);
+    free_dev(h->d_cdyn);
+    free_dev(h->d_cprog);
+    free_dev(h->d_cll);
     if (h->copy_event) cudaEventDestroy(h->copy_event);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     cudaStreamDestroy(h->stream);
@@ -893,8 +1091,60 @@ int piqmc_set_global_moves(piqmc_handle h, int enable)
 
 int piqmc_set_variant(piqmc_handle h, int variant)
 {
-    PIQMC_REQUIRE(h != nullptr && variant >= 0 && variant <= 2, PIQMC_EINVAL, "variant must be 0, 1 or 2");
+    PIQMC_REQUIRE(h != nullptr && variant >= 0 && variant <= 3, PIQMC_EINVAL, "variant must be 0, 1, 2 or 3");
     h->variant = variant;
+    return PIQMC_OK;
+}
+
+int piqmc_set_chain(piqmc_handle h, int chain_len)
+{
+    USE(h);
+    PIQMC_REQUIRE(chain_len >= 0, PIQMC_EINVAL, "chain_len must be >= 0 (0 = choose)");
+    h->chain_force_C = chain_len;
+    if (h->nspins > 0 && h->ncolors > 0) {
+        PIQMC_CUDA(cudaStreamSynchronize(h->stream));
+        TRY(build_chain_plan(h));
+        PIQMC_REQUIRE(chain_len == 0 || h->chain_C > 0, PIQMC_EINVAL,
+                      "no chain plan: the colouring is not the natural order's, maxnb > 4, or chain_len < 4");
+    }
+    return PIQMC_OK;
+}
+
+int piqmc_chain_plan(int nspins, int maxnb, const int32_t *idx, const double *J, int chain_len, uint8_t *kinds,
+                     uint32_t *loc, double *period)
+{
+    PIQMC_REQUIRE(nspins > 0 && maxnb > 0 && maxnb <= 4 && idx && J && chain_len >= 0, PIQMC_EINVAL,
+                  "bad arguments (the chain pipeline needs maxnb <= 4)");
+    const size_t ne = (size_t)nspins * maxnb;
+    std::vector<float> j32(ne);
+    std::vector<uint8_t> live(ne);
+    for (size_t e = 0; e < ne; e++) {
+        PIQMC_REQUIRE(idx[e] >= 0 && idx[e] < nspins, PIQMC_EINVAL, "neighbour index out of range");
+        j32[e] = (float)J[e];
+        live[e] = (idx[e] != (int32_t)(e / maxnb) && J[e] != 0.0) ? 1 : 0;
+    }
+    const GraphView gv = {nspins, maxnb, idx, j32.data(), live.data()};
+    std::vector<PiqmcChainStat> st;
+    double per = 0.0;
+    const int C = choose_chain(&gv, chain_len, st, per);
+    if (C > 0) {
+        for (int i = 0; i < nspins; i++)
+            for (int z = 0; z < 4; z++) {
+                if (kinds) kinds[(size_t)i * 4 + z] = (uint8_t)((st[i].kinds >> (8 * z)) & 0xFFu);
+                if (loc) loc[(size_t)i * 4 + z] = st[i].loc[z];
+            }
+    }
+    if (period) *period = per;
+    return C;
+}
+
+int piqmc_chain_info(piqmc_handle h, int *chain_len, int *nchains, double *period, int *selected)
+{
+    PIQMC_REQUIRE(h != nullptr, PIQMC_EINVAL, "null handle");
+    if (chain_len) *chain_len = h->chain_C;
+    if (nchains) *nchains = h->chain_n;
+    if (period) *period = h->chain_period;
+    if (selected) *selected = chain_selected(h, 1, 0) ? 1 : 0;
     return PIQMC_OK;
 }
 
@@ -911,7 +1161,8 @@ int piqmc_qa_colour(piqmc_handle h, const double *sched, int nsched, int mcsteps
     PIQMC_REQUIRE((float)slices * temp != 0.0f && temp != 0.0f, PIQMC_EZERODIV, "float division");
     PIQMC_REQUIRE(!h->global_moves || piqmc_fast_ok(h, 1, trotter), PIQMC_EINVAL,
                   "world-line moves need the table kernel (maxnb <= 4, variant != 1, >= 32 rows)");
-    PIQMC_REQUIRE(h->seg_S == 1 || (piqmc_fast_ok(h, 1, trotter) && trotter == 0 && !h->global_moves), PIQMC_EINVAL,
+    PIQMC_REQUIRE(h->seg_S == 1 || ((piqmc_fast_ok(h, 1, trotter) || (!orders && chain_selected(h, 1, trotter))) &&
+                                    trotter == 0 && !h->global_moves), PIQMC_EINVAL,
                   "several replicas per word need the table kernel (maxnb <= 4, variant != 1, >= 32 rows), the "
                   "reference Trotter neighbours and no world-line moves");
     std::vector<float> jp2(std::max(nsched, 1)), invT(std::max(nsched, 1), 1.0f / temp);

@@ -39,6 +39,8 @@ struct FastArgs {
     uint32_t k0, k1, row0, sweep0, tag0;
     unsigned int ticket_base;   // units handed out by earlier launches of the same run
     unsigned int poll_ns;       // back-off between polls of a completion flag (0 = spin)
+    unsigned int *err;          // watchdog word: a wait that outlasts watchdog_ns sets it and gives up
+    unsigned long long watchdog_ns;
     int force_generic;          // testing: evaluate every decision function by the generic pattern loop
     uint64_t valid, top;        // lane masks: all `lanes` slices / the last slice (kernel constants: no per-pass arithmetic)
     // several replicas per word (SEG): seg_S segments of seg_P lanes; masks of the first, second and last lane of
@@ -110,8 +112,21 @@ __global__ void __launch_bounds__(FAST_THREADS, MINB) colour_sweep_fast(const Fa
             }
             if (must) {
                 const uint32_t *flag = a.done + (size_t)j * a.nchunks + chunk;
-                while ((int32_t)(ld_acquire(flag) - want) < 0)
+                unsigned int polls = 0;
+                unsigned long long t0 = 0ull;
+                while ((int32_t)(ld_acquire(flag) - want) < 0) {
                     if (a.poll_ns) __nanosleep(a.poll_ns);
+                    if ((++polls & 4095u) == 0u) {             // watchdog: an error, not a hang (the unit then
+                        unsigned long long now;                // runs on stale inputs; the host discards the state)
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                        if (t0 == 0ull) t0 = now;
+                        if (*(volatile unsigned int *)a.err != 0u) break;
+                        if (now - t0 > a.watchdog_ns) {
+                            atomicCAS(a.err, 0u, 1u);
+                            break;
+                        }
+                    }
+                }
             }
         }
     }
@@ -345,6 +360,30 @@ __global__ void __launch_bounds__(FAST_THREADS, MINB) colour_sweep_fast(const Fa
 
 }  // namespace
 
+// rows per block: the per-spin table is built once per block, so more rows per block is less
+// overhead, but fewer independent chunks; keep >= 4 chunks when the state allows
+// (measured on B200, 256x256 P=64: 4 chunks is the sweet spot from 512 to 4096 rows)
+static int fast_rows_per_block(const piqmc_ctx *c)
+{
+    int rpb = 512;
+    while (rpb > FAST_THREADS && (c->nrows + rpb - 1) / rpb < 4) rpb >>= 1;
+    if (const char *e = getenv("PIQMC_ROWS_PER_BLOCK")) {          // tuning knob
+        const int v = atoi(e);
+        if (v >= FAST_THREADS && v % FAST_THREADS == 0) rpb = v;
+    }
+    return rpb;
+}
+
+// One launch holds (sweeps + ramp periods) * N * chunks units; the ticket arithmetic is 32-bit and a
+// grid has at most 2^31 - 1 blocks.  A colouring with many levels and a small level gap (a path graph
+// in natural order) can exceed that even for one sweep: the caller then takes another kernel.
+bool launch_fast_fits(const piqmc_ctx *c, int nperiods_extra)
+{
+    const int rpb = fast_rows_per_block(c);
+    const size_t per_sweep = (size_t)c->nspins * ((c->nrows + rpb - 1) / rpb);
+    return (size_t)(1 + nperiods_extra) * per_sweep < ((size_t)1 << 31);
+}
+
 // Runs `nsweeps` sweeps in as few launches as the grid-size limit allows (normally one).
 // members/level: device arrays, level-major spin order and level per spin; either one list for
 // all sweeps or one per sweep.  d_jp2/d_invT: per sweep.
@@ -353,15 +392,7 @@ int launch_fast_sweeps(piqmc_ctx *c, int qa, int trotter, int nsweeps, const Piq
                        uint64_t seed, uint32_t row0, uint32_t sweep0)
 {
     if (nsweeps <= 0) return PIQMC_OK;
-    // rows per block: the per-spin table is built once per block, so more rows per block is less
-    // overhead, but fewer independent chunks; keep >= 4 chunks when the state allows
-    // (measured on B200, 256x256 P=64: 4 chunks is the sweet spot from 512 to 4096 rows)
-    int rpb = 512;
-    while (rpb > FAST_THREADS && (c->nrows + rpb - 1) / rpb < 4) rpb >>= 1;
-    if (const char *e = getenv("PIQMC_ROWS_PER_BLOCK")) {          // tuning knob
-        const int v = atoi(e);
-        if (v >= FAST_THREADS && v % FAST_THREADS == 0) rpb = v;
-    }
+    const int rpb = fast_rows_per_block(c);
     const int nchunks = (c->nrows + rpb - 1) / rpb;
     const size_t nflags = (size_t)c->nspins * nchunks;
     if (c->flow_nchunks != nchunks || c->d_done == nullptr) {
@@ -375,6 +406,10 @@ int launch_fast_sweeps(piqmc_ctx *c, int qa, int trotter, int nsweeps, const Piq
     }
     if (!c->d_ticket) {
         PIQMC_CUDA(cudaMalloc(&c->d_ticket, sizeof(unsigned int)));
+    }
+    if (!c->d_err) {
+        PIQMC_CUDA(cudaMalloc(&c->d_err, sizeof(unsigned int)));
+        PIQMC_CUDA(cudaMemsetAsync(c->d_err, 0, sizeof(unsigned int), c->stream));
     }
     PIQMC_CUDA(cudaMemsetAsync(c->d_ticket, 0, sizeof(unsigned int), c->stream));
 
@@ -408,8 +443,14 @@ int launch_fast_sweeps(piqmc_ctx *c, int qa, int trotter, int nsweeps, const Piq
     if (const char *e = getenv("PIQMC_POLL_NS")) a.poll_ns = (unsigned int)atoi(e);
     a.force_generic = 0;
     if (const char *e = getenv("PIQMC_FORCE_GENERIC_FN")) a.force_generic = atoi(e);
+    a.err = c->d_err;
+    a.watchdog_ns = 20000000000ull;
+    if (const char *e = getenv("PIQMC_WATCHDOG_MS")) a.watchdog_ns = (unsigned long long)atoll(e) * 1000000ull;
 
     const size_t per_sweep = nflags;
+    PIQMC_REQUIRE(launch_fast_fits(c, nperiods_extra), PIQMC_EINVAL,
+                  "colouring with %d ramp periods x %zu units per sweep does not fit one launch of the dataflow kernel",
+                  nperiods_extra, per_sweep);
     const int max_sweeps = (int)std::max<long long>(1, (long long)(((size_t)1 << 30) / per_sweep) - nperiods_extra);
     unsigned int ticket_base = 0;
     for (int s0 = 0; s0 < nsweeps; s0 += max_sweeps) {

@@ -44,6 +44,39 @@ struct alignas(16) PiqmcUnitRec {
 };
 static_assert(sizeof(PiqmcUnitRec) == 48, "PiqmcUnitRec must be 48 bytes");
 
+// ---- chain kernel (chain_kernels.cu) --------------------------------------------------------
+// The sequential (natural-order) sweep is cut into contiguous chains of C spins; one warp walks one
+// chain for 32 rows.  Per spin (static, graph only): where each of the 4 sorted table columns gets
+// its neighbour word from.
+enum : uint32_t {
+    PIQMC_K_ZERO = 0,      // self entry / unused column: reads as 0
+    PIQMC_K_PREV = 1,      // spin i-1 of the same chain: the word this thread has just written
+    PIQMC_K_NEXT = 2,      // spin i+1 of the same chain: the own word of the next step (old value)
+    PIQMC_K_LL_CUR = 3,    // same position in the preceding chain, this sweep: hand-over ring
+    PIQMC_K_LL_OLD = 4,    // same position in the last chain (chain 0 only), previous sweep: hand-over ring
+    PIQMC_K_MEM_SELF = 5,  // elsewhere in the same chain: state word, no wait
+    PIQMC_K_MEM_CUR = 6,   // another chain, earlier in the order: state word of this sweep (wait for progress)
+    PIQMC_K_MEM_OLD = 7,   // another chain, later in the order: state word of the previous sweep (wait)
+};
+struct alignas(16) PiqmcChainStat {
+    uint32_t loc[4];      // slot k: (chain << 16) | position in chain of the neighbour (kinds >= 3)
+    uint32_t kinds;       // byte k: PIQMC_K_* of slot k (slots = table columns sorted by |J| descending)
+    uint32_t pad;         // as PiqmcUnitRec::pad
+    float J01[2];         // sorted couplings 0, 1 (2, 3 travel in PiqmcChainDyn)
+    float J23[2];
+    uint32_t spare[2];
+};
+static_assert(sizeof(PiqmcChainStat) == 48, "PiqmcChainStat must be 48 bytes");
+// Per (schedule step, spin): the decision functions by name, written by chain_tables_kernel.
+struct alignas(16) PiqmcChainDyn {
+    uint8_t names[8];     // byte 2c = "accept by sign" of Trotter class c, 2c+1 = "... or needs a uniform"
+    uint16_t lane1[4];    // truth tables hacc[0], hacc[1], hall[0], hall[1]
+    uint16_t hacc2, hall2;
+    float J23[2];         // sorted couplings 2, 3 (copied from the static record: one staged record has all)
+    uint32_t spare;
+};
+static_assert(sizeof(PiqmcChainDyn) == 32, "PiqmcChainDyn must be 32 bytes");
+
 // ------------------------------------------------------------------------------------------
 // device context
 // ------------------------------------------------------------------------------------------
@@ -75,6 +108,19 @@ struct piqmc_ctx {
     unsigned int *d_ticket = nullptr;
     int flow_nchunks = 0;
     uint32_t flow_tag = 0;
+    unsigned int *d_err = nullptr;  // watchdog word of the dataflow / chain kernels (0 = fine)
+    // chain kernel (chain_kernels.cu): natural-order sweep cut into chains of chain_C spins
+    int chain_ok = 0;               // the colouring is a level colouring of the natural order, maxnb <= 4
+    int chain_force_C = 0;          // piqmc_set_chain: 0 = choose, > 0 = this chain length
+    int chain_C = 0, chain_n = 0;   // chain length, chains per ring (0: no plan)
+    double chain_period = 0.0;      // modelled steps per sweep of the chain pipeline (host estimate)
+    PiqmcChainStat *d_cstat = nullptr;
+    PiqmcChainDyn *d_cdyn = nullptr;
+    size_t cdyn_elems = 0;
+    uint32_t *d_cprog = nullptr;
+    size_t cprog_elems = 0;
+    void *d_cll = nullptr;
+    size_t cll_bytes = 0;
 
     // packed state.  QA states with at most 32 slices may hold several replicas per word: seg_S
     // segments of seg_P lanes each (lanes = seg_P * seg_S); replica of (row, segment g) = row*seg_S + g
@@ -167,12 +213,19 @@ int launch_energy_coo(piqmc_ctx *c, int nspins, int nnz, const int32_t *d_row, c
 int launch_fast_sweeps(piqmc_ctx *c, int qa, int trotter, int nsweeps, const PiqmcUnitRec *d_recs,
                        int nperiods_extra, int per_sweep_lists, const float *d_jp2, const float *d_invT,
                        uint64_t seed, uint32_t row0, uint32_t sweep0);
-// variant: 0 auto (fast kernel when the graph qualifies and there are enough rows to fill its
-// 128-thread blocks), 1 generic, 2 fast whenever the graph qualifies (used by the parity tests)
+bool launch_fast_fits(const piqmc_ctx *c, int nperiods_extra);   // the grid of one launch stays below 2^31 units
+// chain kernel: nsweeps natural-order sweeps, one launch (chain_kernels.cu).  jp2/invT: host arrays per
+// schedule step; sweep s of the run belongs to schedule step s / mcsteps.
+int launch_chain_sweeps(piqmc_ctx *c, int qa, int nsched, int mcsteps, const float *h_jp2, const float *h_invT,
+                        uint64_t seed, uint32_t row0, uint32_t sweep0);
+int piqmc_check_watchdog(piqmc_ctx *c, const char *what);
+// variant: 0 auto (chain pipeline for natural-order colourings, else the dataflow kernel when the graph
+// qualifies and there are enough rows to fill its 128-thread blocks), 1 generic, 2 dataflow kernel whenever
+// the graph qualifies, 3 chain pipeline whenever there is a plan, else as 2 (2, 3: used by the parity tests)
 static inline bool piqmc_fast_ok(const piqmc_ctx *c, int qa, int trotter)
 {
     (void)qa;
     (void)trotter;
     if (c->variant == 1 || c->maxnb > 4) return false;
-    return c->variant == 2 || c->nrows >= 32;
+    return c->variant >= 2 || c->nrows >= 32;
 }

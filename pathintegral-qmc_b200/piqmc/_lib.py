@@ -70,6 +70,9 @@ SIGNATURES = {
     "piqmc_qa_colour": (c_int, [c_void, c_void, c_int, c_int, c_f, c_u64, c_u32, c_u32, c_int, c_void]),
     "piqmc_sa_colour": (c_int, [c_void, c_void, c_int, c_int, c_u64, c_u32, c_u32, c_void]),
     "piqmc_set_variant": (c_int, [c_void, c_int]),
+    "piqmc_set_chain": (c_int, [c_void, c_int]),
+    "piqmc_chain_info": (c_int, [c_void, P(c_int), P(c_int), P(c_d), P(c_int)]),
+    "piqmc_chain_plan": (c_int, [c_int, c_int, c_void, c_void, c_int, c_void, c_void, P(c_d)]),
     "piqmc_set_global_moves": (c_int, [c_void, c_int]),
     "piqmc_energy": (c_int, [c_void, c_void]),
     "piqmc_results": (c_int, [c_void, c_void, c_void]),

@@ -92,6 +92,17 @@ class Device:
         check(lib.piqmc_set_variant(self._h, int(variant)))
         self.variant = int(variant)
 
+    def set_chain(self, chain_len=0):
+        """Chain pipeline: 0 = let the library choose the chain length, > 0 = force it (and the kernel)."""
+        check(lib.piqmc_set_chain(self._h, int(chain_len)))
+
+    def chain_info(self):
+        """(chain length, chains per ring, modelled steps per sweep, selected) of the current plan;
+        (0, 0, 0.0, False) if there is none.  selected: a static-colouring QA/SA run takes the pipeline."""
+        c, n, per, sel = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_double(0.0), ctypes.c_int(0)
+        check(lib.piqmc_chain_info(self._h, ctypes.byref(c), ctypes.byref(n), ctypes.byref(per), ctypes.byref(sel)))
+        return c.value, n.value, per.value, bool(sel.value)
+
     def set_global_moves(self, enable):
         """World-line (all-slices) moves after the local moves of every spin (QA, maxnb <= 4)."""
         check(lib.piqmc_set_global_moves(self._h, 1 if enable else 0))
@@ -414,6 +425,21 @@ def order_levels(nbs, order=None):
     if rc < 0:
         check(rc)
     return level
+
+
+def chain_plan(nbs, chain_len=0):
+    """Host-side plan of the chain pipeline for the natural-order sweep of `nbs` (piqmc_chain_plan, no
+    device needed): (chain length, kinds uint8[N,4], loc uint32[N,4], modelled steps per sweep)."""
+    idx, J = split_nbs(nbs)
+    n = idx.shape[0]
+    kinds = np.zeros((n, 4), dtype=np.uint8)
+    loc = np.zeros((n, 4), dtype=np.uint32)
+    per = ctypes.c_double(0.0)
+    rc = lib.piqmc_chain_plan(n, idx.shape[1], _ptr(idx), _ptr(J), int(chain_len), _ptr(kinds), _ptr(loc),
+                              ctypes.byref(per))
+    if rc < 0:
+        check(rc)
+    return rc, kinds, loc, per.value
 
 
 def device_count():

@@ -176,13 +176,17 @@ def QuantumAnnealReplicas(sched, mcsteps, slices, temp, nspins, spins0, nbs, see
         if (slices <= 32 and slices % 4 == 0 and TROTTER[trotter] == 0 and not global_moves
                 and d.maxnb <= 4 and d.variant != 1):
             S = 64 // slices
-            # Packing divides the rows by S.  That pays when a wavefront step (one colour class, all
-            # rows) still offers several times the words the GPU holds in flight (~170k); with many
-            # small classes (natural order on a small lattice) the sweep is bound by the dependency
-            # chain and fewer rows only make it worse (measured: tools/bench_configs.py).
+            # Chain pipeline (natural-order colourings): a warp walks a chain for 32 words whatever they
+            # hold, so packing S replicas per word is S times the work at the same cost -- always pack.
+            # Dataflow kernel: packing divides the rows by S.  That pays when a wavefront step (one colour
+            # class, all rows) still offers several times the words the GPU holds in flight (~170k); with
+            # many small classes the sweep is bound by the dependency chain and fewer rows only make it
+            # worse (measured: tools/bench_configs.py).
+            chain = orders is None and d.chain_info()[3]
             nclasses = (int(np.max(color)) + 1) if orders is None else 16
             per_step = max(1, int(nspins) // nclasses)
-            while S > 1 and d.variant != 2 and ((R + S - 1) // S < 32 or per_step * ((R + S - 1) // S) < 350000):
+            while (S > 1 and not chain and d.variant < 2
+                   and ((R + S - 1) // S < 32 or per_step * ((R + S - 1) // S) < 350000)):
                 S -= 1
     else:
         S = int(per_word)

@@ -1,0 +1,32 @@
+#!/bin/bash
+# first GPU contact of the chain pipeline: parity, then quick throughput at 4096 and 512 rows
+export PIQMC_WATCHDOG_MS=8000
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/smi.txt
+timeout 1200 python -m pytest tests/test_gpu_chain.py -x -q > gpurun_out/t_chain.log 2>&1
+echo "chain tests rc=$?" >> gpurun_out/t_chain.log
+tail -5 gpurun_out/t_chain.log
+for mb in 4 3; do
+  for R in 4096 512; do
+    PIQMC_CHAIN_MINB=$mb timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu --replicas $R > gpurun_out/b_chain_mb${mb}_R$R.log 2>&1
+    echo "mb=$mb R=$R rc=$?"; python - <<PY
+import json
+try:
+    d=json.loads(open("gpurun_out/b_chain_mb${mb}_R$R.log").read().strip().splitlines()[-1])
+    print("value %.3e ms/step %.3f e2e %.3e" % (d["value"], d["ms_per_step"], d["e2e"]["value"]), d["e2e"].get("breakdown_s"))
+except Exception as e:
+    print("parse failed", e); print(open("gpurun_out/b_chain_mb${mb}_R$R.log").read()[-1500:])
+PY
+  done
+done
+for R in 4096 512; do
+  timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu --replicas $R --variant 2 > gpurun_out/b_flow_R$R.log 2>&1
+  python - <<PY
+import json
+try:
+    d=json.loads(open("gpurun_out/b_flow_R$R.log").read().strip().splitlines()[-1])
+    print("dataflow R=$R value %.3e ms/step %.3f" % (d["value"], d["ms_per_step"]))
+except Exception as e:
+    print("parse failed", e)
+PY
+done
