@@ -195,23 +195,25 @@ int piqmc_set_global_moves(piqmc_handle h, int enable);
  * 2 = dataflow kernel (one unit per (sweep, spin, row chunk); falls back to generic when the graph
  * does not qualify), 3 = chain pipeline (natural-order colourings with maxnb <= 4; falls back to 2) */
 int piqmc_set_variant(piqmc_handle h, int variant);
-/* Chain pipeline (the natural-order sweep of qmc.pyx:320-357 cut into contiguous chains of chain_len
- * spins, one warp per chain and 32 rows): chain_len = 0 lets the library choose (a lattice row);
- * > 0 forces that length and the pipeline (testing, tuning).  piqmc_chain_info reports the plan of
- * the current graph + colouring: chain_len = 0 when there is none (colouring is not the natural
- * order's, or maxnb > 4); period = modelled pipeline steps per sweep; selected = 1 when a static-colouring run
- * (reference Trotter neighbours, no world-line moves) would take the pipeline under the current variant. */
+/* Chain pipeline (the natural-order sweep of qmc.pyx:320-357 on a 2-D lattice, cut into chains of
+ * chain_len consecutive spins -- a lattice row --, one warp per chain and 32 or 64 rows): chain_len = 0
+ * lets the library choose; > 0 forces that length and the pipeline (testing, tuning).
+ * piqmc_chain_info reports the plan of the current graph + colouring: chain_len = 0 when there is none
+ * (the colouring is not the natural order's, maxnb > 4, or some coupled pair is neither consecutive in
+ * a chain, nor the two ends of a chain, nor the same position of adjacent chains / of the first and
+ * last chain); period = pipeline steps per sweep; selected = 1 when a static-colouring run (reference
+ * Trotter neighbours, no world-line moves) would take the pipeline under the current variant and state. */
 int piqmc_set_chain(piqmc_handle h, int chain_len);
 int piqmc_chain_info(piqmc_handle h, int *chain_len, int *nchains, double *period, int *selected);
 /* The plan itself, on the host (no device needed): for the natural-order sweep of the ELL table
  * (idx, J) cut into chains of chain_len spins (0 = choose), kinds[i*4 + k] is where sorted table
- * column k of spin i (columns sorted by |J| descending, stable) gets its neighbour word from
- * (0 none, 1 the word just written, 2 the next own word, 3/4 hand-over ring of the preceding chain
- * for this / the previous sweep, 5 state word of the own chain, 6/7 progress-guarded state word of
- * another chain for this / the previous sweep), loc[i*4 + k] = (chain << 16) | position of that
- * neighbour.  Returns the chain length (0: no plan, < 0: error). */
+ * column k of spin i (columns sorted by |J| descending, stable) gets its neighbour word from:
+ * 0 none, 1 the word this chain wrote one step earlier, 2 the own-row word one step later, 3 the
+ * same position of the preceding chain (chain 0 of a torus: the last chain, previous sweep), 4 the
+ * same position of the following chain (last chain of a torus: chain 0, this sweep).  *wrap = 1
+ * when the first and last chain are coupled.  Returns the chain length (0: no plan, < 0: error). */
 int piqmc_chain_plan(int nspins, int maxnb, const int32_t *idx, const double *J, int chain_len,
-                     uint8_t *kinds, uint32_t *loc, double *period);
+                     uint8_t *kinds, int *wrap);
 
 /* sa.ClassicalIsingEnergy (piqmc/sa.pyx:25-44) of every (row, lane) of the resident state,
  * float64: energies[row*lanes + lane].  energies may be NULL (result stays on the device). */

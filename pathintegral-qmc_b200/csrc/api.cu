@@ -161,8 +161,11 @@ static void build_unit_recs(const piqmc_ctx *h, const int32_t *level, const int3
 
 
 // ---- chain plan (chain_kernels.cu) -------------------------------------------------------------
-// The natural-order sweep cut into contiguous chains of C spins.  Slot kinds of spin i (sorted
-// columns, as in build_unit_recs): see PIQMC_K_* in common.cuh.
+// The natural-order sweep of a 2-D lattice cut into chains of C consecutive spins.  Slot kinds of spin i
+// (sorted columns, as in build_unit_recs): see PIQMC_K_* in common.cuh.  A graph qualifies when every
+// coupled pair is one of: consecutive spins of a chain, the two ends of a chain (a chain that closes
+// on itself), the same position of consecutive chains, or the same position of the first and the last
+// chain (a torus).
 struct GraphView {            // host view of an ELL table (float32 couplings, live = coupled to another spin)
     int nspins, maxnb;
     const int32_t *h_idx;
@@ -170,11 +173,15 @@ struct GraphView {            // host view of an ELL table (float32 couplings, l
     const uint8_t *h_live;
 };
 
-static void build_chain_stat(const GraphView *h, int C, std::vector<PiqmcChainStat> &out)
+// false: some coupled pair does not fit the pattern; *wrap: the last chain is coupled to chain 0
+static bool build_chain_stat(const GraphView *h, int C, std::vector<PiqmcChainStat> &out, int *wrap)
 {
     const int N = h->nspins, mb = h->maxnb < 4 ? h->maxnb : 4;
-    const int nchains = (N + C - 1) / C;
+    if (C < 8 || N % C != 0) return false;
+    const int nchains = N / C;
+    if (nchains > 65535) return false;
     out.assign(N, PiqmcChainStat());
+    *wrap = 0;
     for (int i = 0; i < N; i++) {
         int32_t nb[4];
         float J[4];
@@ -192,148 +199,119 @@ static void build_chain_stat(const GraphView *h, int C, std::vector<PiqmcChainSt
                 }
             }
         }
+        for (int n = 4; n < h->maxnb; n++)
+            if (h->h_live[(size_t)i * h->maxnb + n]) return false;
         int col[4] = {0, 1, 2, 3};
         std::stable_sort(col, col + 4, [&](int a, int b) { return fabsf(J[a]) > fabsf(J[b]); });
         PiqmcChainStat &r = out[i];
         const int ci = i / C, pi = i % C;
-        const int pred = ci == 0 ? nchains - 1 : ci - 1;
         uint32_t kinds = 0, pad = 0;
-        float Js[4];
         for (int z = 0; z < 4; z++) {
             const int n = col[z];
-            Js[z] = J[n];
+            r.J[z] = J[n];
             pad |= (uint32_t)n << (2 * z);
             if (J[n] < 0.0f) pad |= 1u << (8 + z);
             uint32_t kind = PIQMC_K_ZERO;
-            r.loc[z] = 0;
             if (livef[n]) {
-                const int j = nb[n], cj = j / C, pj = j % C;
-                if (cj == ci) kind = (j == i - 1) ? PIQMC_K_PREV : (j == i + 1 ? PIQMC_K_NEXT : PIQMC_K_MEM_SELF);
-                else if (pj == pi && cj == pred) kind = j < i ? PIQMC_K_LL_CUR : PIQMC_K_LL_OLD;
-                else kind = j < i ? PIQMC_K_MEM_CUR : PIQMC_K_MEM_OLD;
-                r.loc[z] = ((uint32_t)cj << 16) | (uint32_t)pj;
+                const int j = nb[n];
+                if (j == i - 1 && pi > 0) kind = PIQMC_K_LEFT;
+                else if (j == i + 1 && pi < C - 1) kind = PIQMC_K_RIGHT;
+                else if (j == i + C - 1 && pi == 0) kind = PIQMC_K_LEFT;          // closed chain, first spin
+                else if (j == i - (C - 1) && pi == C - 1) kind = PIQMC_K_RIGHT;   // closed chain, last spin
+                else if (j == i - C) kind = PIQMC_K_UP;
+                else if (j == i + C) kind = PIQMC_K_DOWN;
+                else if (j == i + (N - C) && ci == 0) {
+                    kind = PIQMC_K_UP;
+                    *wrap = 1;
+                } else if (j == i - (N - C) && ci == nchains - 1) {
+                    kind = PIQMC_K_DOWN;
+                    *wrap = 1;
+                } else return false;
             }
             kinds |= kind << (8 * z);
         }
         r.kinds = kinds;
         r.pad = pad;
-        r.J01[0] = Js[0];
-        r.J01[1] = Js[1];
-        r.J23[0] = Js[2];
-        r.J23[1] = Js[3];
         r.spare[0] = r.spare[1] = 0;
     }
+    return true;
 }
 
-// Modelled period (in steps of one warp) of the chain pipeline in steady state: event times of three
-// sweeps with unit step cost, a hand-over costing LL and a progress-guarded state word costing MEM
-// (publication every 8 steps + an L2 round trip).  c = C for a perfect pipeline.
-static double chain_model_period(const GraphView *h, const std::vector<PiqmcChainStat> &st, int C)
-{
-    const int N = h->nspins;
-    const double LL = 0.3, MEM = 6.0;
-    std::vector<double> prev(N, 0.0), cur(N, 0.0);
-    double period = 0.0;
-    for (int s = 0; s < 3; s++) {
-        for (int i = 0; i < N; i++) {
-            double t = (i % C) ? cur[i - 1] : (s ? prev[std::min(N - 1, i + C - 1 - (i % C))] : 0.0);
-            for (int z = 0; z < 4; z++) {
-                const uint32_t kind = (st[i].kinds >> (8 * z)) & 0xFFu;
-                if (kind < PIQMC_K_LL_CUR) continue;
-                const int j = (int)(st[i].loc[z] >> 16) * C + (int)(st[i].loc[z] & 0xFFFFu);
-                double d = 0.0;
-                switch (kind) {
-                case PIQMC_K_LL_CUR: d = cur[j] + LL; break;
-                case PIQMC_K_LL_OLD: d = s ? prev[j] + LL : 0.0; break;
-                case PIQMC_K_MEM_CUR: d = cur[j] + MEM; break;
-                case PIQMC_K_MEM_OLD: d = s ? prev[j] + MEM : 0.0; break;
-                default: break;
-                }
-                if (d > t) t = d;
-            }
-            cur[i] = t + 1.0;
-        }
-        if (s == 2)
-            for (int i = 0; i < N; i++) period = std::max(period, cur[i] - prev[i]);
-        prev.swap(cur);
-    }
-    return period;
-}
-
-// Choose the chain length (or take the forced one) and upload the static records.  Candidates: the
-// most frequent index distances of coupled pairs (a lattice row), and one chain for everything.
-static int choose_chain(const GraphView *h, int force_C, std::vector<PiqmcChainStat> &best, double &best_period)
+// Choose the chain length (or take the forced one) and build the static records.  Candidates: the
+// most frequent index distances of coupled pairs (a lattice row).
+static int choose_chain(const GraphView *h, int force_C, std::vector<PiqmcChainStat> &best, double &best_period,
+                        int *wrap)
 {
     const int N = h->nspins;
     std::vector<int> cand;
     if (force_C > 0) cand.push_back(std::min(force_C, N));
     else {
         std::vector<std::pair<int, int>> hist;                 // (distance, count)
-        {
-            std::vector<int> d;
-            for (int i = 0; i < N; i++)
-                for (int n = 0; n < h->maxnb; n++) {
-                    const size_t e = (size_t)i * h->maxnb + n;
-                    if (h->h_live[e] && h->h_idx[e] > i + 1) d.push_back(h->h_idx[e] - i);
-                }
-            std::sort(d.begin(), d.end());
-            for (size_t k = 0; k < d.size();) {
-                size_t m = k;
-                while (m < d.size() && d[m] == d[k]) m++;
-                hist.push_back({d[k], (int)(m - k)});
-                k = m;
+        std::vector<int> d;
+        for (int i = 0; i < N; i++)
+            for (int n = 0; n < h->maxnb; n++) {
+                const size_t e = (size_t)i * h->maxnb + n;
+                if (h->h_live[e] && h->h_idx[e] > i + 1) d.push_back(h->h_idx[e] - i);
             }
-            std::sort(hist.begin(), hist.end(), [](const std::pair<int, int> &a, const std::pair<int, int> &b) {
-                return a.second != b.second ? a.second > b.second : a.first < b.first;
-            });
+        std::sort(d.begin(), d.end());
+        for (size_t k = 0; k < d.size();) {
+            size_t m = k;
+            while (m < d.size() && d[m] == d[k]) m++;
+            hist.push_back({d[k], (int)(m - k)});
+            k = m;
         }
+        std::sort(hist.begin(), hist.end(), [](const std::pair<int, int> &a, const std::pair<int, int> &b) {
+            return a.second != b.second ? a.second > b.second : a.first < b.first;
+        });
         for (size_t k = 0; k < hist.size() && cand.size() < 3; k++) cand.push_back(hist[k].first);
         cand.push_back(N);
     }
     best_period = 0.0;
-    int best_C = 0;
     for (int C : cand) {
-        if (C < 4 || C > 65535 || (N + C - 1) / C > 65535) continue;
-        if (N - ((N + C - 1) / C - 1) * C < 2 && (N + C - 1) / C > 1) continue;      // a last chain of one spin: the
-                                                                                     // kernel requests own words 2 steps ahead
         std::vector<PiqmcChainStat> st;
-        build_chain_stat(h, C, st);
-        const double period = chain_model_period(h, st, C);
-        if (best_C == 0 || period < best_period) {
-            best_period = period;
-            best_C = C;
-            best.swap(st);
-        }
+        int w = 0;
+        if (!build_chain_stat(h, C, st, &w)) continue;
+        best.swap(st);
+        *wrap = w;
+        best_period = (double)std::max(C, w ? N / C : 1);      // steps per sweep of the rigid ring
+        return C;
     }
-    return best_C;
+    return 0;
 }
 
 static int build_chain_plan(piqmc_ctx *h)
 {
-    h->chain_C = h->chain_n = 0;
+    h->chain_C = h->chain_n = h->chain_wrap = 0;
     if (!h->chain_ok) return PIQMC_OK;
     const int N = h->nspins;
     const GraphView gv = {N, h->maxnb, h->h_idx.data(), h->h_J32.data(), h->h_live.data()};
     std::vector<PiqmcChainStat> best;
     double best_period = 0.0;
-    const int best_C = choose_chain(&gv, h->chain_force_C, best, best_period);
+    int wrap = 0;
+    const int best_C = choose_chain(&gv, h->chain_force_C, best, best_period, &wrap);
     if (best_C == 0) return PIQMC_OK;
     if (!h->d_cstat) PIQMC_CUDA(cudaMalloc(&h->d_cstat, (size_t)N * sizeof(PiqmcChainStat)));
     PIQMC_CUDA(cudaMemcpy(h->d_cstat, best.data(), (size_t)N * sizeof(PiqmcChainStat), cudaMemcpyHostToDevice));
     h->chain_C = best_C;
-    h->chain_n = (N + best_C - 1) / best_C;
+    h->chain_n = N / best_C;
+    h->chain_wrap = wrap;
     h->chain_period = best_period;
     return PIQMC_OK;
 }
 
-// Which kernel runs a static colouring: the chain pipeline when the colouring is the natural order's
-// and its modelled critical path (steps of ~0.6 us) beats the dataflow kernel's (levels of ~3.6 us).
+// Which kernel runs a static colouring.  The chain pipeline is opt-in (variant 3, piqmc_set_chain, or
+// PIQMC_CHAIN=1): measured on B200 it equals the dataflow kernel when few rows make the sweep
+// latency-bound and loses when many rows make it throughput-bound.
 static bool chain_selected(const piqmc_ctx *h, int qa, int trotter)
 {
-    if (h->chain_C < 4 || h->variant == 1 || h->variant == 2 || h->global_moves || (qa && trotter)) return false;
-    if (h->variant == 3 || h->chain_force_C > 0) return true;
-    if (const char *e = getenv("PIQMC_CHAIN")) return atoi(e) != 0;
-    return h->chain_period <= 6.0 * (double)h->ncolors;
+    if (h->chain_C < 8 || h->variant == 1 || h->variant == 2 || h->global_moves || (qa && trotter)) return false;
+    if (h->variant != 3 && h->chain_force_C == 0) {
+        const char *e = getenv("PIQMC_CHAIN");
+        if (!e || atoi(e) == 0) return false;
+    }
+    if (h->d_words == nullptr) return true;                    // no state yet: the plan exists
+    ChainGeom g;
+    return chain_geometry(h, qa, &g);
 }
 
 static int apply_colouring(piqmc_ctx *h, int ncolors, const int32_t *color, bool validate)
@@ -579,7 +557,9 @@ int piqmc_destroy(piqmc_handle h)
     free_dev(h->d_ticket);
     free_dev(h->d_stage);
     free_dev(h->d_err);
-    free_dev(h->d_cdyn);
+    free_dev(h->d_chot);
+    free_dev(h->d_ccold);
+    free_dev(h->d_cband);
     free_dev(h->d_cprog);
     free_dev(h->d_cll);
     if (h->copy_event) cudaEventDestroy(h->copy_event);
@@ -1105,16 +1085,16 @@ int piqmc_set_chain(piqmc_handle h, int chain_len)
         PIQMC_CUDA(cudaStreamSynchronize(h->stream));
         TRY(build_chain_plan(h));
         PIQMC_REQUIRE(chain_len == 0 || h->chain_C > 0, PIQMC_EINVAL,
-                      "no chain plan: the colouring is not the natural order's, maxnb > 4, or chain_len < 4");
+                      "no chain plan: the colouring is not the natural order's, or the graph is not a lattice of rows of "
+                      "chain_len spins (chain_len >= 8, dividing the number of spins)");
     }
     return PIQMC_OK;
 }
 
 int piqmc_chain_plan(int nspins, int maxnb, const int32_t *idx, const double *J, int chain_len, uint8_t *kinds,
-                     uint32_t *loc, double *period)
+                     int *wrap)
 {
-    PIQMC_REQUIRE(nspins > 0 && maxnb > 0 && maxnb <= 4 && idx && J && chain_len >= 0, PIQMC_EINVAL,
-                  "bad arguments (the chain pipeline needs maxnb <= 4)");
+    PIQMC_REQUIRE(nspins > 0 && maxnb > 0 && idx && J && chain_len >= 0, PIQMC_EINVAL, "bad arguments");
     const size_t ne = (size_t)nspins * maxnb;
     std::vector<float> j32(ne);
     std::vector<uint8_t> live(ne);
@@ -1126,15 +1106,12 @@ int piqmc_chain_plan(int nspins, int maxnb, const int32_t *idx, const double *J,
     const GraphView gv = {nspins, maxnb, idx, j32.data(), live.data()};
     std::vector<PiqmcChainStat> st;
     double per = 0.0;
-    const int C = choose_chain(&gv, chain_len, st, per);
-    if (C > 0) {
+    int w = 0;
+    const int C = choose_chain(&gv, chain_len, st, per, &w);
+    if (C > 0 && kinds)
         for (int i = 0; i < nspins; i++)
-            for (int z = 0; z < 4; z++) {
-                if (kinds) kinds[(size_t)i * 4 + z] = (uint8_t)((st[i].kinds >> (8 * z)) & 0xFFu);
-                if (loc) loc[(size_t)i * 4 + z] = st[i].loc[z];
-            }
-    }
-    if (period) *period = per;
+            for (int z = 0; z < 4; z++) kinds[(size_t)i * 4 + z] = (uint8_t)((st[i].kinds >> (8 * z)) & 0xFFu);
+    if (wrap) *wrap = w;
     return C;
 }
 

@@ -45,37 +45,35 @@ struct alignas(16) PiqmcUnitRec {
 static_assert(sizeof(PiqmcUnitRec) == 48, "PiqmcUnitRec must be 48 bytes");
 
 // ---- chain kernel (chain_kernels.cu) --------------------------------------------------------
-// The sequential (natural-order) sweep is cut into contiguous chains of C spins; one warp walks one
-// chain for 32 rows.  Per spin (static, graph only): where each of the 4 sorted table columns gets
-// its neighbour word from.
+// The sequential (natural-order) sweep of a 2-D lattice is cut into chains of C consecutive spins (a
+// lattice row); one warp walks one chain.  Per spin (static, graph only): where each of the 4 sorted
+// table columns gets its neighbour word from.
 enum : uint32_t {
     PIQMC_K_ZERO = 0,      // self entry / unused column: reads as 0
-    PIQMC_K_PREV = 1,      // spin i-1 of the same chain: the word this thread has just written
-    PIQMC_K_NEXT = 2,      // spin i+1 of the same chain: the own word of the next step (old value)
-    PIQMC_K_LL_CUR = 3,    // same position in the preceding chain, this sweep: hand-over ring
-    PIQMC_K_LL_OLD = 4,    // same position in the last chain (chain 0 only), previous sweep: hand-over ring
-    PIQMC_K_MEM_SELF = 5,  // elsewhere in the same chain: state word, no wait
-    PIQMC_K_MEM_CUR = 6,   // another chain, earlier in the order: state word of this sweep (wait for progress)
-    PIQMC_K_MEM_OLD = 7,   // another chain, later in the order: state word of the previous sweep (wait)
+    PIQMC_K_LEFT = 1,      // the spin visited one step earlier by this chain: spin i-1, or -- for the first
+                           // spin of a chain that closes on itself -- the chain's last spin (its old value)
+    PIQMC_K_RIGHT = 2,     // the spin visited one step later: spin i+1 (old value), or -- for the last spin
+                           // of a closed chain -- the chain's first spin (its new value)
+    PIQMC_K_UP = 3,        // same position in the preceding chain, this sweep; for chain 0 of a torus: in
+                           // the last chain, previous sweep
+    PIQMC_K_DOWN = 4,      // same position in the following chain, previous sweep; for the last chain of a
+                           // torus: in chain 0, this sweep
 };
 struct alignas(16) PiqmcChainStat {
-    uint32_t loc[4];      // slot k: (chain << 16) | position in chain of the neighbour (kinds >= 3)
-    uint32_t kinds;       // byte k: PIQMC_K_* of slot k (slots = table columns sorted by |J| descending)
+    float J[4];           // couplings of the table columns sorted by |J| descending (stable), 0 for unused
+    uint32_t kinds;       // byte k: PIQMC_K_* of sorted slot k
     uint32_t pad;         // as PiqmcUnitRec::pad
-    float J01[2];         // sorted couplings 0, 1 (2, 3 travel in PiqmcChainDyn)
-    float J23[2];
     uint32_t spare[2];
 };
-static_assert(sizeof(PiqmcChainStat) == 48, "PiqmcChainStat must be 48 bytes");
-// Per (schedule step, spin): the decision functions by name, written by chain_tables_kernel.
-struct alignas(16) PiqmcChainDyn {
-    uint8_t names[8];     // byte 2c = "accept by sign" of Trotter class c, 2c+1 = "... or needs a uniform"
-    uint16_t lane1[4];    // truth tables hacc[0], hacc[1], hall[0], hall[1]
-    uint16_t hacc2, hall2;
-    float J23[2];         // sorted couplings 2, 3 (copied from the static record: one staged record has all)
-    uint32_t spare;
+static_assert(sizeof(PiqmcChainStat) == 32, "PiqmcChainStat must be 32 bytes");
+// Per (schedule step, spin), written by chain_tables_kernel: a 16-byte record the sweep reads every
+// step {names of "accept by sign" / "... or needs a uniform" of Trotter classes 0, 1 | class 2, flags |
+// sign bytes of the sorted couplings | kinds * 16} and a 16-byte record of truth tables for the rare
+// function outside the list of 27.
+struct ChainGeom {
+    int rpt, cw, nbands, nrings;
+    size_t smem;
 };
-static_assert(sizeof(PiqmcChainDyn) == 32, "PiqmcChainDyn must be 32 bytes");
 
 // ------------------------------------------------------------------------------------------
 // device context
@@ -113,10 +111,13 @@ struct piqmc_ctx {
     int chain_ok = 0;               // the colouring is a level colouring of the natural order, maxnb <= 4
     int chain_force_C = 0;          // piqmc_set_chain: 0 = choose, > 0 = this chain length
     int chain_C = 0, chain_n = 0;   // chain length, chains per ring (0: no plan)
-    double chain_period = 0.0;      // modelled steps per sweep of the chain pipeline (host estimate)
+    int chain_wrap = 0;             // the last chain is coupled to chain 0 (torus)
+    double chain_period = 0.0;      // pipeline steps per sweep: max(chain length, chains) on a torus
     PiqmcChainStat *d_cstat = nullptr;
-    PiqmcChainDyn *d_cdyn = nullptr;
-    size_t cdyn_elems = 0;
+    uint4 *d_chot = nullptr, *d_ccold = nullptr;   // per (schedule step, spin) records of the current launch
+    size_t chot_elems = 0, ccold_elems = 0;
+    int *d_cband = nullptr;         // first chain of every band
+    size_t cband_elems = 0;
     uint32_t *d_cprog = nullptr;
     size_t cprog_elems = 0;
     void *d_cll = nullptr;
@@ -219,6 +220,8 @@ bool launch_fast_fits(const piqmc_ctx *c, int nperiods_extra);   // the grid of 
 int launch_chain_sweeps(piqmc_ctx *c, int qa, int nsched, int mcsteps, const float *h_jp2, const float *h_invT,
                         uint64_t seed, uint32_t row0, uint32_t sweep0);
 int piqmc_check_watchdog(piqmc_ctx *c, const char *what);
+// launch geometry of the chain pipeline for the current plan and state; false: it cannot run them
+bool chain_geometry(const piqmc_ctx *c, int qa, ChainGeom *g);
 // variant: 0 auto (chain pipeline for natural-order colourings, else the dataflow kernel when the graph
 // qualifies and there are enough rows to fill its 128-thread blocks), 1 generic, 2 dataflow kernel whenever
 // the graph qualifies, 3 chain pipeline whenever there is a plan, else as 2 (2, 3: used by the parity tests)

@@ -102,31 +102,29 @@ def check(h, steps):
         assert val == (h >> p) & 1, (hex(h), steps)
 
 
-def emit():
-    for h in CANON:
-        check(h, plan(h))
-    out = []
-    w = out.append
-    w("// GENERATED by gen_canon.py -- do not edit.  The 27 regular functions of 4 ordered variables,")
-    w("// one PTX jump table (brx.idx), minimal LOP3 sequences for both 32-lane halves.")
-    w("#define PIQMC_NCANON 27")
-    w("#define PIQMC_CANON_TABLES " + ", ".join("0x%04xu" % h for h in CANON))
-    w("// operands: %0 lo, %1 hi (out); %2 fid; %3..%6 z0..z3 low halves; %7..%10 z0..z3 high halves")
-    w("#define PIQMC_CANON_EVAL_ASM \\")
+def emit_asm(w, macro, ngroups):
+    """one jump table evaluating the function for `ngroups` independent 32-lane groups: outputs
+    %0..%(g-1), function id %g, then z0..z3 of group j at %(g+1+4j)..%(g+4+4j)"""
+    g = ngroups
+    w("// operands: %%0..%%%d out (one per 32-lane group); %%%d fid; z0..z3 of group j at %%(%d+4j)..%%(%d+4j)"
+      % (g - 1, g, g + 1, g + 4))
+    w("#define %s \\" % macro)
     w('    "{\\n\\t" \\')
-    w('    ".reg .b32 t0, t1, u0, u1;\\n\\t" \\')
+    w('    ".reg .b32 t0, t1;\\n\\t" \\')
     w('    "ts: .branchtargets ' + ", ".join("C%d" % k for k in range(27)) + ';\\n\\t" \\')
-    w('    "brx.idx %2, ts;\\n\\t" \\')
+    w('    "brx.idx %%%d, ts;\\n\\t" \\' % g)
     nl = {}
     for k, h in enumerate(CANON):
         steps = plan(h)
         nl[k] = 0 if steps[0][0] == "const" else len(steps)
         w('    "C%d:\\n\\t" \\' % k)
-        for half, (dst, tmp0, tmp1, base) in enumerate((("%0", "t0", "t1", 3), ("%1", "u0", "u1", 7))):
+        for grp in range(g):
+            dst, base = "%%%d" % grp, g + 1 + 4 * grp
+
             def opnd(s):
                 if s[0] == "z":
                     return "%%%d" % (base + int(s[1]))
-                return {"t0": tmp0, "t1": tmp1, "f": dst}[s]
+                return {"t0": "t0", "t1": "t1", "f": dst}[s]
             for st in steps:
                 if st[0] == "const":
                     w('    "mov.b32 %s, 0x%08x;\\n\\t" \\' % (dst, st[1]))
@@ -136,6 +134,22 @@ def emit():
         w('    "bra.uni DONE;\\n\\t" \\')
     w('    "DONE:\\n\\t" \\')
     w('    "}"')
+    return nl
+
+
+def emit():
+    for h in CANON:
+        check(h, plan(h))
+    out = []
+    w = out.append
+    w("// GENERATED by gen_canon.py -- do not edit.  The 27 regular functions of 4 ordered variables,")
+    w("// one PTX jump table (brx.idx) per macro, minimal LOP3 sequences per 32-lane group.")
+    w("#define PIQMC_NCANON 27")
+    w("#define PIQMC_CANON_TABLES " + ", ".join("0x%04xu" % h for h in CANON))
+    w("// one 64-lane word: groups = (low half, high half)")
+    nl = emit_asm(w, "PIQMC_CANON_EVAL_ASM", 2)
+    w("// two 64-lane words (two rows per thread): groups = (row 0 low, row 0 high, row 1 low, row 1 high)")
+    emit_asm(w, "PIQMC_CANON_EVAL_ASM2", 4)
     w("// LOP3 per 32 lanes: " + ", ".join("%04x:%d" % (h, nl[k]) for k, h in enumerate(CANON)))
     return "\n".join(out) + "\n"
 

@@ -72,7 +72,7 @@ SIGNATURES = {
     "piqmc_set_variant": (c_int, [c_void, c_int]),
     "piqmc_set_chain": (c_int, [c_void, c_int]),
     "piqmc_chain_info": (c_int, [c_void, P(c_int), P(c_int), P(c_d), P(c_int)]),
-    "piqmc_chain_plan": (c_int, [c_int, c_int, c_void, c_void, c_int, c_void, c_void, P(c_d)]),
+    "piqmc_chain_plan": (c_int, [c_int, c_int, c_void, c_void, c_int, c_void, P(c_int)]),
     "piqmc_set_global_moves": (c_int, [c_void, c_int]),
     "piqmc_energy": (c_int, [c_void, c_void]),
     "piqmc_results": (c_int, [c_void, c_void, c_void]),

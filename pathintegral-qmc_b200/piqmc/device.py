@@ -429,17 +429,17 @@ def order_levels(nbs, order=None):
 
 def chain_plan(nbs, chain_len=0):
     """Host-side plan of the chain pipeline for the natural-order sweep of `nbs` (piqmc_chain_plan, no
-    device needed): (chain length, kinds uint8[N,4], loc uint32[N,4], modelled steps per sweep)."""
+    device needed): (chain length, kinds uint8[N,4], wrap).  kinds[i, k]: where sorted table column k of
+    spin i gets its neighbour word from (0 none, 1 previous step of the chain, 2 next own-row word,
+    3 preceding chain, 4 following chain); wrap: first and last chain are coupled."""
     idx, J = split_nbs(nbs)
     n = idx.shape[0]
     kinds = np.zeros((n, 4), dtype=np.uint8)
-    loc = np.zeros((n, 4), dtype=np.uint32)
-    per = ctypes.c_double(0.0)
-    rc = lib.piqmc_chain_plan(n, idx.shape[1], _ptr(idx), _ptr(J), int(chain_len), _ptr(kinds), _ptr(loc),
-                              ctypes.byref(per))
+    wrap = ctypes.c_int(0)
+    rc = lib.piqmc_chain_plan(n, idx.shape[1], _ptr(idx), _ptr(J), int(chain_len), _ptr(kinds), ctypes.byref(wrap))
     if rc < 0:
         check(rc)
-    return rc, kinds, loc, per.value
+    return rc, kinds, bool(wrap.value)
 
 
 def device_count():
