@@ -31,7 +31,7 @@ for _p in (ROOT, PKG):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
-L, P, R_TOTAL, TEMP = 256, 64, 4096, 0.01
+L, P, R_TOTAL, TEMP = 256, 64, 4096, float(os.environ.get("PIQMC_BENCH_TEMP", "0.01"))   # (env: experiments only)
 GAMMA0, GAMMA1 = 1.5, 1e-8
 SEED = 2024
 B_ALG_HBM = 0.25        # bytes/attempt: each 64-slice word read once + written once per sweep

@@ -278,33 +278,6 @@ __device__ __noinline__ uint64_t rare_generic(const LatArgs &a, uint32_t f, uint
     return eval_generic(h, z0, z1, z2, z3);
 }
 
-// function `fid` (warp-uniform, one of the 27) of the 4 masks of RPT words at once: one indexed jump
-template <int RPT>
-__device__ __forceinline__ void eval_canon(uint32_t fid, const uint64_t (&z)[RPT][4], uint64_t (&out)[RPT])
-{
-    if (RPT == 1) {
-        uint32_t lo, hi;
-        asm(PIQMC_CANON_EVAL_ASM
-            : "=&r"(lo), "=&r"(hi)
-            : "r"(fid), "r"((uint32_t)z[0][0]), "r"((uint32_t)z[0][1]), "r"((uint32_t)z[0][2]), "r"((uint32_t)z[0][3]),
-              "r"((uint32_t)(z[0][0] >> 32)), "r"((uint32_t)(z[0][1] >> 32)), "r"((uint32_t)(z[0][2] >> 32)),
-              "r"((uint32_t)(z[0][3] >> 32)));
-        out[0] = ((uint64_t)hi << 32) | lo;
-    } else {
-        uint32_t o0, o1, o2, o3;
-        asm(PIQMC_CANON_EVAL_ASM2
-            : "=&r"(o0), "=&r"(o1), "=&r"(o2), "=&r"(o3)
-            : "r"(fid), "r"((uint32_t)z[0][0]), "r"((uint32_t)z[0][1]), "r"((uint32_t)z[0][2]), "r"((uint32_t)z[0][3]),
-              "r"((uint32_t)(z[0][0] >> 32)), "r"((uint32_t)(z[0][1] >> 32)), "r"((uint32_t)(z[0][2] >> 32)),
-              "r"((uint32_t)(z[0][3] >> 32)), "r"((uint32_t)z[RPT - 1][0]), "r"((uint32_t)z[RPT - 1][1]),
-              "r"((uint32_t)z[RPT - 1][2]), "r"((uint32_t)z[RPT - 1][3]), "r"((uint32_t)(z[RPT - 1][0] >> 32)),
-              "r"((uint32_t)(z[RPT - 1][1] >> 32)), "r"((uint32_t)(z[RPT - 1][2] >> 32)),
-              "r"((uint32_t)(z[RPT - 1][3] >> 32)));
-        out[0] = ((uint64_t)o1 << 32) | o0;
-        out[RPT - 1] = ((uint64_t)o3 << 32) | o2;
-    }
-}
-
 // ---- decision functions of every (schedule step, spin), once for all replicas ----------------------
 // hot record: x = names fa0 fb0 fa1 fb1 (fa: "accept by sign", fb: "... or needs a uniform" of a Trotter
 // class), y = fa2 | fb2 << 8 | flags << 16 (bit 0: some fb is not FID_NONE, bit 1: some name is
