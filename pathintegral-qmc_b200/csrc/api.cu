@@ -49,6 +49,9 @@ void free_graph(piqmc_ctx *c)
     free_dev(c->d_recs);
     free_dev(c->d_done);
     free_dev(c->d_cstat);
+    free_dev(c->d_lstat);
+    free_dev(c->d_lvoff);
+    c->lv_period = c->lv_width = 0;
     c->chain_ok = c->chain_C = c->chain_n = 0;
     c->flow_nchunks = 0;
     c->color_off.clear();
@@ -314,6 +317,38 @@ static bool chain_selected(const piqmc_ctx *h, int qa, int trotter)
     return chain_geometry(h, qa, &g);
 }
 
+// the sorted couplings and pad of every spin (level-synchronous kernel: decision tables, thresholds)
+static int upload_level_stat(piqmc_ctx *h)
+{
+    free_dev(h->d_lstat);
+    if (h->maxnb > 4) return PIQMC_OK;
+    std::vector<int32_t> zero(h->nspins, 0), ident(h->nspins);
+    for (int i = 0; i < h->nspins; i++) ident[i] = i;
+    std::vector<PiqmcUnitRec> recs(h->nspins);
+    build_unit_recs(h, zero.data(), ident.data(), nullptr, recs.data());
+    std::vector<PiqmcChainStat> st(h->nspins);
+    for (int i = 0; i < h->nspins; i++) {
+        for (int z = 0; z < 4; z++) st[i].J[z] = recs[i].J[z];
+        st[i].kinds = 0;
+        st[i].pad = (uint32_t)recs[i].pad;
+        st[i].spare[0] = st[i].spare[1] = 0;
+    }
+    PIQMC_CUDA(cudaMalloc(&h->d_lstat, st.size() * sizeof(PiqmcChainStat)));
+    PIQMC_CUDA(cudaMemcpy(h->d_lstat, st.data(), st.size() * sizeof(PiqmcChainStat), cudaMemcpyHostToDevice));
+    return PIQMC_OK;
+}
+
+// The level-synchronous kernel runs any level colouring of a graph with maxnb <= 4 (reference Trotter
+// neighbours, no world-line moves).  Opt-in for now: variant 4 or PIQMC_LEVEL=1.
+static bool level_selected(const piqmc_ctx *h, int qa, int trotter)
+{
+    if (h->maxnb > 4 || !h->d_lstat || h->global_moves || (qa && trotter)) return false;
+    if (h->variant == 4) return true;
+    if (h->variant != 0) return false;
+    const char *e = getenv("PIQMC_LEVEL");
+    return e && atoi(e) != 0;
+}
+
 static int apply_colouring(piqmc_ctx *h, int ncolors, const int32_t *color, bool validate)
 {
     if (validate) {
@@ -356,6 +391,21 @@ static int apply_colouring(piqmc_ctx *h, int ncolors, const int32_t *color, bool
         std::vector<PiqmcUnitRec> recs(h->nspins);
         build_unit_recs(h, color, pm.data(), po.data(), recs.data());
         PIQMC_CUDA(cudaMemcpy(h->d_recs, recs.data(), recs.size() * sizeof(PiqmcUnitRec), cudaMemcpyHostToDevice));
+        // level-synchronous kernel: where the steps of a period (members with the same level mod D) begin
+        // in the period-major list
+        const int Dp = std::min(D, ncolors);
+        std::vector<int> off(Dp + 1, 0);
+        for (int i = 0; i < h->nspins; i++) off[color[i] % D + 1]++;
+        int width = 0;
+        for (int r = 0; r < Dp; r++) {
+            width = std::max(width, off[r + 1]);
+            off[r + 1] += off[r];
+        }
+        free_dev(h->d_lvoff);
+        PIQMC_CUDA(cudaMalloc(&h->d_lvoff, off.size() * sizeof(int)));
+        PIQMC_CUDA(cudaMemcpy(h->d_lvoff, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice));
+        h->lv_period = Dp;
+        h->lv_width = width;
     }
     h->flow_extra = (ncolors + D - 1) / D - 1;
     h->ncolors = ncolors;
@@ -419,9 +469,13 @@ static int run_colour_sweeps(piqmc_ctx *h, int qa, int trotter, int nsched, int 
     if (nsweeps == 0) return PIQMC_OK;
     // static colourings with many levels and a small level gap (a path graph in natural order) would need
     // more units than one grid holds: those run class by class (or through the chain pipeline below)
-    const bool fast = piqmc_fast_ok(h, qa, trotter) && (orders || launch_fast_fits(h, h->flow_extra));
+    const bool use_level = level_selected(h, qa, trotter);
+    const bool fast = !use_level && piqmc_fast_ok(h, qa, trotter) && (orders || launch_fast_fits(h, h->flow_extra));
     if (!orders) PIQMC_REQUIRE(h->ncolors > 0, PIQMC_ENOGRAPH, "graph has no colouring");
     else TRY(check_orders(N, nsweeps, orders));
+    if (!orders && use_level)
+        return launch_level_sweeps(h, qa, (int)nsweeps, mcsteps, 0, jp2.data(), invT.data(), nsched, seed, row0, sweep0,
+                                   h->d_recs, h->d_lvoff, nullptr, h->lv_period, h->flow_extra, 0, h->lv_width);
 
     // per-sweep parameters (fast path)
     DevBuf<float> d_jp2, d_invT;
@@ -460,14 +514,16 @@ static int run_colour_sweeps(piqmc_ctx *h, int qa, int trotter, int nsched, int 
 
     // per-sweep visiting orders: level-colour each sweep on the host, ship member lists (and
     // levels) in chunks of sweeps (bounded device memory)
+    const bool wantrec = fast || use_level;
     const size_t chunk = std::max<size_t>(1, std::min<size_t>(nsweeps, (size_t)(64u << 20) /
-                                                                        ((size_t)N * (fast ? sizeof(PiqmcUnitRec) : 4))));
+                                                                        ((size_t)N * (wantrec ? sizeof(PiqmcUnitRec) : 4))));
     DevBuf<int32_t> d_mem;
     DevBuf<PiqmcUnitRec> d_rec;
-    if (fast) PIQMC_CUDA(d_rec.alloc(chunk * N));
-    else      PIQMC_CUDA(d_mem.alloc(chunk * N));
+    DevBuf<int> d_soff, d_ssweep;
+    if (wantrec) PIQMC_CUDA(d_rec.alloc(chunk * N));
+    else         PIQMC_CUDA(d_mem.alloc(chunk * N));
     std::vector<int32_t> members(chunk * N), levels(chunk * N);
-    std::vector<PiqmcUnitRec> recs(fast ? chunk * N : 0);
+    std::vector<PiqmcUnitRec> recs(wantrec ? chunk * N : 0);
     std::vector<std::vector<int>> offs(chunk);
     for (size_t base = 0; base < nsweeps; base += chunk) {
         const size_t m = std::min(chunk, nsweeps - base);
@@ -476,9 +532,36 @@ static int run_colour_sweeps(piqmc_ctx *h, int qa, int trotter, int nsched, int 
             const int nlev = order_levels(N, h->maxnb, h->h_idx.data(), h->h_live.data(),
                                           orders + (base + s) * N, lev);
             bucket_members(N, nlev, lev, offs[s], members.data() + s * N);
-            if (fast) build_unit_recs(h, lev, members.data() + s * N, nullptr, recs.data() + s * N);
+            if (wantrec) build_unit_recs(h, lev, members.data() + s * N, nullptr, recs.data() + s * N);
         }
         PIQMC_CUDA(cudaStreamSynchronize(h->stream));     // previous chunk's lists no longer in use
+        if (use_level) {
+            // steps = the levels of every sweep of the chunk, in order
+            std::vector<int> soff, ssweep;
+            int width = 1;
+            for (size_t s = 0; s < m; s++)
+                for (size_t c = 0; c + 1 < offs[s].size(); c++) {
+                    soff.push_back((int)(s * N) + offs[s][c]);
+                    ssweep.push_back((int)s);
+                    width = std::max(width, offs[s][c + 1] - offs[s][c]);
+                }
+            soff.push_back((int)(m * N));
+            if (d_soff.p) cudaFree(d_soff.p), d_soff.p = nullptr;
+            if (d_ssweep.p) cudaFree(d_ssweep.p), d_ssweep.p = nullptr;
+            PIQMC_CUDA(d_soff.alloc(soff.size()));
+            PIQMC_CUDA(d_ssweep.alloc(ssweep.size()));
+            PIQMC_CUDA(cudaMemcpyAsync(d_rec.p, recs.data(), m * N * sizeof(PiqmcUnitRec), cudaMemcpyHostToDevice,
+                                       h->stream));
+            PIQMC_CUDA(cudaMemcpyAsync(d_soff.p, soff.data(), soff.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+            PIQMC_CUDA(cudaMemcpyAsync(d_ssweep.p, ssweep.data(), ssweep.size() * sizeof(int), cudaMemcpyHostToDevice,
+                                       h->stream));
+            const int f0 = (int)(base / mcsteps), foff = (int)(base % mcsteps);
+            const int nfc = (int)((foff + m + mcsteps - 1) / mcsteps);
+            TRY(launch_level_sweeps(h, qa, (int)m, mcsteps, foff, jp2.data() + f0, invT.data() + f0, nfc, seed, row0,
+                                    sweep0 + (uint32_t)base, d_rec.p, d_soff.p, d_ssweep.p, 0, 0, (int)ssweep.size(),
+                                    width));               // synchronises the stream before it returns
+            continue;
+        }
         if (fast) {
             PIQMC_CUDA(cudaMemcpyAsync(d_rec.p, recs.data(), m * N * sizeof(PiqmcUnitRec), cudaMemcpyHostToDevice,
                                        h->stream));
@@ -712,6 +795,7 @@ int piqmc_set_graph(piqmc_handle h, int nspins, int maxnb, const int32_t *idx, c
     PIQMC_CUDA(cudaMalloc(&h->d_members, (size_t)nspins * sizeof(int32_t)));
     PIQMC_CUDA(cudaMalloc(&h->d_level, (size_t)nspins * sizeof(int32_t)));
     PIQMC_CUDA(cudaMalloc(&h->d_recs, (size_t)nspins * sizeof(PiqmcUnitRec)));
+    TRY(upload_level_stat(h));
     if (color) TRY(apply_colouring(h, ncolors, color, false));
     // a resident state stays valid for a new graph on the same spins (words are [spin][row],
     // whatever the couplings): the SA pre-anneal -> PIQMC hand-over may change the colouring
@@ -1071,7 +1155,7 @@ int piqmc_set_global_moves(piqmc_handle h, int enable)
 
 int piqmc_set_variant(piqmc_handle h, int variant)
 {
-    PIQMC_REQUIRE(h != nullptr && variant >= 0 && variant <= 3, PIQMC_EINVAL, "variant must be 0, 1, 2 or 3");
+    PIQMC_REQUIRE(h != nullptr && variant >= 0 && variant <= 4, PIQMC_EINVAL, "variant must be 0 ... 4");
     h->variant = variant;
     return PIQMC_OK;
 }

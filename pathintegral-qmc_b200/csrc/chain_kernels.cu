@@ -855,17 +855,7 @@ __global__ void __launch_bounds__(LT_MAXW * 32, 1) chain_sweep(const LatArgs a)
 }
 
 template <typename T>
-int grow(T *&p, size_t &have, size_t want, cudaStream_t stream)
-{
-    if (want <= have && p) return PIQMC_OK;
-    PIQMC_CUDA(cudaStreamSynchronize(stream));
-    if (p) PIQMC_CUDA(cudaFree(p));
-    p = nullptr;
-    have = 0;
-    PIQMC_CUDA(cudaMalloc(&p, want * sizeof(T)));
-    have = want;
-    return PIQMC_OK;
-}
+int grow(T *&p, size_t &have, size_t want, cudaStream_t stream) { return piqmc_grow(p, have, want, stream); }
 
 size_t chain_smem_bytes(int cw, int rpt)
 {
@@ -887,6 +877,17 @@ int env_int(const char *name, int dflt)
 }
 
 }  // namespace
+
+int launch_decision_tables(piqmc_ctx *c, int qa, const PiqmcChainStat *d_stat, int nf, const float *d_jp2,
+                           const float *d_invT, int force_generic)
+{
+    const unsigned tgrid = (unsigned)(((size_t)nf * c->nspins + 3) / 4);
+    if (qa) chain_tables_kernel<true><<<tgrid, 128, 0, c->stream>>>(d_stat, (uint4 *)c->d_chot, (uint4 *)c->d_ccold, d_jp2, d_invT, c->nspins, nf, force_generic);
+    else    chain_tables_kernel<false><<<tgrid, 128, 0, c->stream>>>(d_stat, (uint4 *)c->d_chot, (uint4 *)c->d_ccold, d_jp2, d_invT, c->nspins, nf, force_generic);
+    c->launches++;
+    PIQMC_CUDA(cudaGetLastError());
+    return PIQMC_OK;
+}
 
 int piqmc_check_watchdog(piqmc_ctx *c, const char *what)
 {

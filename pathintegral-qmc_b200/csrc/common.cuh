@@ -122,6 +122,10 @@ struct piqmc_ctx {
     size_t cprog_elems = 0;
     void *d_cll = nullptr;
     size_t cll_bytes = 0;
+    // level-synchronous kernel (level_kernels.cu): steps of the period-major member order
+    PiqmcChainStat *d_lstat = nullptr;   // [N] sorted couplings + pad of every spin (any graph with maxnb <= 4)
+    int *d_lvoff = nullptr;              // [lv_period + 1] offsets of the steps of one period into d_recs
+    int lv_period = 0, lv_width = 0;     // steps per period, members of the widest step
 
     // packed state.  QA states with at most 32 slices may hold several replicas per word: seg_S
     // segments of seg_P lanes each (lanes = seg_P * seg_S); replica of (row, segment g) = row*seg_S + g
@@ -220,11 +224,35 @@ bool launch_fast_fits(const piqmc_ctx *c, int nperiods_extra);   // the grid of 
 int launch_chain_sweeps(piqmc_ctx *c, int qa, int nsched, int mcsteps, const float *h_jp2, const float *h_invT,
                         uint64_t seed, uint32_t row0, uint32_t sweep0);
 int piqmc_check_watchdog(piqmc_ctx *c, const char *what);
+// decision functions of every (schedule step, spin), once for all replicas: c->d_chot / c->d_ccold
+// (chain_kernels.cu; d_jp2 / d_invT: device arrays of nf schedule steps)
+int launch_decision_tables(piqmc_ctx *c, int qa, const PiqmcChainStat *d_stat, int nf, const float *d_jp2,
+                           const float *d_invT, int force_generic);
+// level-synchronous sweeps (level_kernels.cu)
+int launch_level_sweeps(piqmc_ctx *c, int qa, int nsweeps, int mcsteps, int f_off, const float *h_jp2,
+                        const float *h_invT, int nf_all, uint64_t seed, uint32_t row0, uint32_t sweep0,
+                        const PiqmcUnitRec *d_recs, const int *d_step_off, const int *d_step_sweep, int period_len,
+                        int nperiods_extra, int nsteps_lists, int width);
+void level_geometry(const piqmc_ctx *c, int width, int *warps, int *K);
+
+// grow-only device buffer
+template <typename T>
+int piqmc_grow(T *&p, size_t &have, size_t want, cudaStream_t stream)
+{
+    if (want <= have && p) return PIQMC_OK;
+    PIQMC_CUDA(cudaStreamSynchronize(stream));
+    if (p) PIQMC_CUDA(cudaFree(p));
+    p = nullptr;
+    have = 0;
+    PIQMC_CUDA(cudaMalloc(&p, want * sizeof(T)));
+    have = want;
+    return PIQMC_OK;
+}
 // launch geometry of the chain pipeline for the current plan and state; false: it cannot run them
 bool chain_geometry(const piqmc_ctx *c, int qa, ChainGeom *g);
-// variant: 0 auto (chain pipeline for natural-order colourings, else the dataflow kernel when the graph
-// qualifies and there are enough rows to fill its 128-thread blocks), 1 generic, 2 dataflow kernel whenever
-// the graph qualifies, 3 chain pipeline whenever there is a plan, else as 2 (2, 3: used by the parity tests)
+// variant: 0 auto, 1 generic, 2 dataflow kernel whenever the graph qualifies, 3 chain pipeline whenever there
+// is a plan, else as 2, 4 level-synchronous kernel whenever the graph qualifies, else as 2 (2, 3, 4: used by
+// the parity tests)
 static inline bool piqmc_fast_ok(const piqmc_ctx *c, int qa, int trotter)
 {
     (void)qa;
