@@ -51,7 +51,13 @@ void free_graph(piqmc_ctx *c)
     free_dev(c->d_cstat);
     free_dev(c->d_lstat);
     free_dev(c->d_lvoff);
+    free_dev(c->d_xrecs);
+    free_dev(c->d_stream);
+    c->stream_slots = c->stream_len = 0;
+    c->h_recs.clear();
+    c->h_lvoff.clear();
     c->lv_period = c->lv_width = 0;
+    c->lvx_K = c->lvx_W = 0;
     c->chain_ok = c->chain_C = c->chain_n = 0;
     c->flow_nchunks = 0;
     c->color_off.clear();
@@ -406,6 +412,40 @@ static int apply_colouring(piqmc_ctx *h, int ncolors, const int32_t *color, bool
         PIQMC_CUDA(cudaMemcpy(h->d_lvoff, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice));
         h->lv_period = Dp;
         h->lv_width = width;
+        h->h_recs = recs;
+        h->h_lvoff = off;
+        free_dev(h->d_stream);                                   // laid out at the next launch
+        h->stream_slots = h->stream_len = 0;
+        // staged variant: one member per warp and step; where every neighbour word was written
+        free_dev(h->d_xrecs);
+        h->lvx_K = h->lvx_W = 0;
+        int xw = 0, xk = 0;
+        if (Dp >= 3 && level_staged_geometry(width, &xw, &xk)) {
+            std::vector<int> pos(h->nspins);                      // position of a spin within its step
+            for (int k = 0; k < h->nspins; k++) pos[pm[k]] = k - off[color[pm[k]] % D];
+            std::vector<PiqmcLevelRec> xr(h->nspins);
+            for (int k = 0; k < h->nspins; k++) {
+                const PiqmcUnitRec &r = recs[k];
+                PiqmcLevelRec &x = xr[k];
+                x.spin = r.spin;
+                x.sweepoff = r.sweepoff;
+                for (int z = 0; z < 4; z++) {
+                    x.nb[z] = r.nb[z];
+                    uint16_t src = 0;
+                    if (r.dep[z] != 0) {
+                        const int j = r.nb[z];
+                        const int gap = r.dep[z] == 2 ? color[r.spin] - color[j] : Dp - (color[j] - color[r.spin]);
+                        if (gap == 1 || gap == 2)
+                            src = (uint16_t)((pos[j] % xw) | ((pos[j] / xw) << 5) | (gap << 10) | (r.dep[z] == 1 ? 1 << 12 : 0));
+                    }
+                    x.src[z] = src;
+                }
+            }
+            PIQMC_CUDA(cudaMalloc(&h->d_xrecs, xr.size() * sizeof(PiqmcLevelRec)));
+            PIQMC_CUDA(cudaMemcpy(h->d_xrecs, xr.data(), xr.size() * sizeof(PiqmcLevelRec), cudaMemcpyHostToDevice));
+            h->lvx_K = xk;
+            h->lvx_W = xw;
+        }
     }
     h->flow_extra = (ncolors + D - 1) / D - 1;
     h->ncolors = ncolors;

@@ -44,6 +44,20 @@ struct alignas(16) PiqmcUnitRec {
 };
 static_assert(sizeof(PiqmcUnitRec) == 48, "PiqmcUnitRec must be 48 bytes");
 
+// ---- level kernel, staged variant (level_kernels.cu) -------------------------------------------------
+// One member of a step: where its words come from.  src[k] of sorted neighbour k: bits 0..4 warp and bits
+// 5..8 block (within the cluster) of the thread that wrote the neighbour's word, bits 10..11 how long ago
+// (0: three or more steps, or never in this launch -- read from global memory; 1: in the step before;
+// 2: two steps before -- both still in the blocks' exchange buffers), bit 12: that write belongs to the
+// previous sweep (in the first sweep of a launch the word is the initial state: global memory).
+struct alignas(16) PiqmcLevelRec {
+    int32_t spin;
+    int32_t sweepoff;     // as PiqmcUnitRec
+    int32_t nb[4];        // as PiqmcUnitRec (sorted by |J|, nspins = the all-zero row)
+    uint16_t src[4];
+};
+static_assert(sizeof(PiqmcLevelRec) == 32, "PiqmcLevelRec must be 32 bytes");
+
 // ---- chain kernel (chain_kernels.cu) --------------------------------------------------------
 // The sequential (natural-order) sweep of a 2-D lattice is cut into chains of C consecutive spins (a
 // lattice row); one warp walks one chain.  Per spin (static, graph only): where each of the 4 sorted
@@ -126,6 +140,12 @@ struct piqmc_ctx {
     PiqmcChainStat *d_lstat = nullptr;   // [N] sorted couplings + pad of every spin (any graph with maxnb <= 4)
     int *d_lvoff = nullptr;              // [lv_period + 1] offsets of the steps of one period into d_recs
     int lv_period = 0, lv_width = 0;     // steps per period, members of the widest step
+    PiqmcLevelRec *d_xrecs = nullptr;    // staged variant: member records with word sources (null: not applicable)
+    int lvx_K = 0, lvx_W = 0;            // its geometry: blocks per cluster, warps per block (one member per warp and step)
+    std::vector<PiqmcUnitRec> h_recs;    // host copy of d_recs and the step offsets (streams are laid out per launch geometry)
+    std::vector<int> h_lvoff;
+    PiqmcLevelRec *d_stream = nullptr;   // streamed variant: [stream_slots][stream_len] records of one period
+    int stream_slots = 0, stream_len = 0;
 
     // packed state.  QA states with at most 32 slices may hold several replicas per word: seg_S
     // segments of seg_P lanes each (lanes = seg_P * seg_S); replica of (row, segment g) = row*seg_S + g
@@ -234,6 +254,7 @@ int launch_level_sweeps(piqmc_ctx *c, int qa, int nsweeps, int mcsteps, int f_of
                         const PiqmcUnitRec *d_recs, const int *d_step_off, const int *d_step_sweep, int period_len,
                         int nperiods_extra, int nsteps_lists, int width);
 void level_geometry(const piqmc_ctx *c, int width, int *warps, int *K);
+bool level_staged_geometry(int width, int *warps, int *K);   // one member per warp and step: K * warps >= width
 
 // grow-only device buffer
 template <typename T>

@@ -1,5 +1,10 @@
 """GPU parity tests of the level-synchronous kernel (csrc/level_kernels.cu): every group of 32 replica
-rows walks the dependency levels of the visiting order on its own thread-block cluster.  It must equal,
+rows walks the dependency levels of the visiting order on its own thread-block cluster -- in two variants:
+the plain one (any colouring, any geometry) and the staged one (static colourings with one member per warp
+and step and an even number of rows: exchange buffers in distributed shared memory, cp.async staging; the
+default when it applies and its clusters fit the device) and the streamed one (static colourings, an even
+number of rows, any number of members per warp and step: per-warp record streams, bulk copies (TMA) into
+staging slots; the default for the rest).  All must equal,
 bit for bit, the CPU statement of the sequential sweep (oracle/piqmc_oracle.c part 3; the order of the
 reference's per-spin-reset variant, piqmc/qmc.pyx:320-357) -- for every geometry (1, 2, 4, 8 blocks per
 cluster, few and many warps, several members per warp and step), QA and SA, one and several replicas per
@@ -62,19 +67,32 @@ def _run_qa(dev, nbs, color, sched, mcsteps, P, T, R, seed, replica0, sweep0, en
     return np.ascontiguousarray(np.transpose(got, (0, 2, 1)))
 
 
-K = lambda k, w=None: dict({"PIQMC_LEVEL_K": str(k)}, **({"PIQMC_LEVEL_WARPS": str(w)} if w else {}))
+def K(k, w=None):
+    """a forced geometry of the plain kernel (the staged and streamed variants are switched off)"""
+    return dict({"PIQMC_LEVEL_K": str(k), "PIQMC_LEVEL_STAGED": "0", "PIQMC_LEVEL_STREAM": "0"},
+                **({"PIQMC_LEVEL_WARPS": str(w)} if w else {}))
+
+
+def KS(k):
+    """the streamed variant with k blocks per cluster"""
+    return {"PIQMC_LEVEL_K": str(k), "PIQMC_LEVEL_STAGED": "0"}
+
+
+PLAIN = {"PIQMC_LEVEL_STAGED": "0", "PIQMC_LEVEL_STREAM": "0"}
+STAGED = {"PIQMC_LEVEL_STAGED": "2"}
 
 CASES = [
     # inst, P, T, sched, mcsteps, R, geometries
-    ("inst_0_32x32", 20, 0.01, (1.5, 1e-8, 25), 1, 6, ({}, K(2), K(8, 4))),                 # config 2 shape
+    ("inst_0_32x32", 20, 0.01, (1.5, 1e-8, 25), 1, 6, ({}, PLAIN, KS(1), KS(2), K(2), K(8, 4))),                 # config 2 shape
     ("inst_0_32x32", 64, 0.01, (1.5, 1e-8, 8), 1, 35, ({}, K(4, 8))),                       # full words, 2 groups (one ragged)
-    ("inst_0_32x32", 64, 0.01, (1.5, 1e-8, 8), 1, 130, (K(1, 3), K(2, 32), K(8, 1))),       # 5 groups; odd warp counts
+    ("inst_0_32x32", 64, 0.01, (1.5, 1e-8, 8), 1, 130, ({}, KS(1), K(1, 3), K(2, 32), K(8, 1))),       # 5 groups; odd warp counts
     ("inst_0_32x32", 33, 0.3, (1.5, 1e-8, 6), 2, 3, ({}, K(4))),                            # odd lanes, hot (many draws)
-    ("inst_0_32x32", 33, 0.3, (1.5, 1e-8, 6), 2, 66, (K(1, 5),)),
-    ("inst_0_32x32", 2, 0.5, (1.5, 1e-3, 6), 2, 70, ({},)),                                 # minimum slices
+    ("inst_0_32x32", 33, 0.3, (1.5, 1e-8, 6), 2, 66, ({}, KS(1), K(1, 5))),
+    ("inst_0_32x32", 2, 0.5, (1.5, 1e-3, 6), 2, 70, ({}, KS(1), PLAIN)),                                 # minimum slices
     ("santoro_80x80", 20, 0.01, (1.5, 1e-8, 4), 1, 2, ({}, K(8))),                          # config 3 shape
-    ("santoro_80x80", 20, 0.01, (1.5, 1e-8, 3), 1, 64, (K(2, 16),)),
-    ("boixo", 5, 0.05, (0.5, 1e-8, 10), 3, 40, ({}, K(2, 2))),                              # config 1: 8 spins, not a lattice
+    ("santoro_80x80", 20, 0.01, (1.5, 1e-8, 3), 1, 64, ({}, KS(1), KS(2), K(2, 16))),
+    ("santoro_80x80", 64, 0.3, (1.5, 1e-8, 3), 2, 34, ({}, KS(1), KS(4))),                               # hot, clusters of 4, ragged group
+    ("boixo", 5, 0.05, (0.5, 1e-8, 10), 3, 40, ({}, PLAIN, KS(1), K(2, 2))),                              # config 1: 8 spins, not a lattice
 ]
 
 
@@ -93,7 +111,7 @@ def test_level_qa_bit_exact(golden, dev, inst, P, T, sch, mcsteps, R, geoms):
 
 
 @pytest.mark.parametrize("order", ["natural", "checkerboard", "permutation"])
-@pytest.mark.parametrize("R,P,env", [(300, 8, {}), (130, 64, K(2)), (33, 20, K(4, 2))])
+@pytest.mark.parametrize("R,P,env", [(300, 8, {}), (300, 8, PLAIN), (300, 8, KS(1)), (130, 64, K(2)), (130, 64, KS(2)), (33, 20, K(4, 2))])
 def test_level_orders_bit_exact(dev, order, R, P, env):
     """All three visiting orders (static level colourings and a fresh permutation per sweep, level-coloured
     on the host per sweep) against the sequential CPU statement; mcsteps = 2 so that sweeps and schedule
@@ -135,8 +153,9 @@ def test_level_generic_function_path(golden, dev):
 @pytest.mark.parametrize("inst,sch,mcsteps,R,geoms", [
     ("inst_0_32x32", (3.0, 0.01, 12), 1, 130, ({}, K(2, 8))),
     ("inst_0_32x32", (3.0, 1.0, 4), 2, 2100, ({},)),            # hot: every thread draws (33 rows)
-    ("inst_0_32x32", (3.0, 1.0, 3), 2, 4100, (K(1, 7),)),
-    ("santoro_80x80", (3.0, 0.01, 3), 1, 65, ({},)),
+    ("inst_0_32x32", (3.0, 1.0, 3), 2, 4100, ({}, KS(1), K(1, 7))),    # hot, 66 rows (staged, streamed, plain)
+    ("santoro_80x80", (3.0, 0.01, 3), 1, 129, ({}, PLAIN)),
+    ("santoro_80x80", (3.0, 0.01, 3), 1, 128, (KS(1), KS(2))),
 ])
 def test_level_sa_bit_exact(golden, dev, inst, sch, mcsteps, R, geoms):
     import piqmc.sa as sa
@@ -203,8 +222,20 @@ def test_level_replicas_per_word_bit_exact(dev, P, R, T):
     assert np.array_equal(many["words"], one["words"]) and np.array_equal(many["energies"], one["energies"])
 
 
-@pytest.mark.parametrize("rows", [4096, 512])
-def test_level_config5_full_size_bit_exact_sampled_replicas(dev, rows):
+def test_level_staged_is_chosen(dev):
+    """Geometry of the staged variant (reported through the launch count: one launch for the tables, one
+    for the sweeps) and the cases it leaves to the plain kernel."""
+    nbs, idx, J32, color, checker = _torus(16, 3)
+    sched = np.linspace(1.5, 1e-8, 4)
+    for R, col in ((64, color), (63, color), (64, checker)):
+        init = O.colour_init_spins(9, 0, R, 256)
+        want = np.repeat(init[:, :, None], 16, axis=2).copy()
+        O.qa_colour(sched, 1, 16, 0.05, idx, J32, col, want, 9, 0, 0, 0)
+        assert np.array_equal(want, _run_qa(dev, nbs, col, sched, 1, 16, 0.05, R, 9, 0, 0, {}))
+
+
+@pytest.mark.parametrize("rows,env", [(4096, {}), (512, {}), (512, KS(8)), (512, PLAIN)])
+def test_level_config5_full_size_bit_exact_sampled_replicas(dev, rows, env):
     """BASELINE configs[4] in the shape bench.py times (256x256 Gaussian torus, P = 64, natural order; 4096
     rows on one GPU = 128 groups on one block each, 512 rows = the 8-GPU shard = 16 groups on clusters of 8),
     compared with the CPU statement for sampled replicas: the Philox key carries the global replica id, so
@@ -217,10 +248,11 @@ def test_level_config5_full_size_bit_exact_sampled_replicas(dev, rows):
     dev.set_graph(nbs, color)
     dev.set_variant(4)
     try:
-        dev.state_alloc(rows, P)
-        dev.state_init_random(seed, replica0, tile=True)
-        dev.qa_colour(sched, 1, 0.01, seed, replica0=replica0)
-        words = dev.state_download_words()                      # [rows, n]
+        with _Env(env):
+            dev.state_alloc(rows, P)
+            dev.state_init_random(seed, replica0, tile=True)
+            dev.qa_colour(sched, 1, 0.01, seed, replica0=replica0)
+            words = dev.state_download_words()                  # [rows, n]
     finally:
         dev.set_variant(0)
     for r in (0, rows // 8 - 1, rows // 2, rows - 1):
