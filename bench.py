@@ -36,10 +36,17 @@ GAMMA0, GAMMA1 = 1.5, 1e-8
 SEED = 2024
 B_ALG_HBM = 0.25        # bytes/attempt: each 64-slice word read once + written once per sweep
 B_ALG_SMEM = 1.0        # bytes/attempt touched on chip: own r+w, 4 neighbours, 2 Trotter bits
-# from the ncu capture under profiles/r1_colour_sweep_fast_ncu.md: DRAM bytes moved per sweep of this
-# workload (read + write = the packed state once each way) and executed warp-instructions per attempt
-NCU_DRAM_BYTES_PER_SWEEP = 4.315e9
-NCU_WINST_PER_ATTEMPT = 0.187
+# from the ncu captures under profiles/: measured DRAM traffic relative to the algorithmic bytes, and executed
+# warp-instructions per attempt, by rows per GPU (the kernel's per-unit overhead weighs more with few rows)
+NCU_CAPTURES = {4096: {"traffic_over_algorithmic": 1.005, "winst_per_attempt": 0.187,
+                       "source": "profiles/r1_colour_sweep_fast_ncu.md (4096 rows per GPU)"},
+                512: {"traffic_over_algorithmic": 0.993, "winst_per_attempt": 0.294,
+                      "source": "profiles/r1_colour_sweep_fast_ncu_512rows.md (512 rows per GPU)"}}
+
+
+def ncu_capture(rows_per_gpu):
+    """the capture whose rows per GPU are closest (log scale) to this run's"""
+    return NCU_CAPTURES[min(NCU_CAPTURES, key=lambda r: abs(np.log(r) - np.log(max(rows_per_gpu, 1))))]
 METRIC = "spin-flip attempts/sec"
 
 
@@ -184,23 +191,24 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "attempts/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": config_dict(args, cores_note="host cores: %d" % cores),
-        "cpu_baseline": {"value": rate, "unit": "attempts/s", "cores": cores, "kind": kind, "sample": sample},
+        "config": config_dict(args),                       # the workload named; what this arm ran of it: cpu_baseline
+        "cpu_baseline": {"value": rate, "unit": "attempts/s", "cores": cores, "kind": kind, "sample": sample,
+                         "replicas_run": cores},
         "e2e": {"value": rate, "unit": "attempts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
 
 
-def config_dict(args, cores_note=None):
-    c = {"workload": "synthetic 256x256 Gaussian 2D Ising torus, P=64 slices, R=4096 replicas total, "
-                     "T=0.01, Gamma 1.5->1e-8 over K steps, mcsteps=1 (BASELINE.json configs[4])",
-         "nspins": L * L, "slices": P, "replicas_total": args.replicas, "order": args.order,
-         "state": "bit-packed uint64 word per (spin, replica), 2.1 GB total",
-         "l2_policy": "inputs larger than L2: per-GPU state %.0f MB >> 126 MB L2 at N<=8" % (R_TOTAL * L * L * 8 / 1e6 / 8)}
-    if cores_note:
-        c["note"] = cores_note
-    return c
+def config_dict(args):
+    state_gb = args.replicas * L * L * 8 / 1e9
+    return {"workload": "synthetic %dx%d Gaussian 2D Ising torus, P=%d slices, R=%d replicas total, "
+                        "T=%g, Gamma 1.5->1e-8 over K steps, mcsteps=1 (BASELINE.json configs[4]%s)"
+                        % (L, L, P, args.replicas, TEMP, "" if args.replicas == 4096 else ", replica count changed"),
+            "nspins": L * L, "slices": P, "replicas_total": args.replicas, "order": args.order,
+            "state": "bit-packed uint64 word per (spin, replica), %.2f GB total" % state_gb,
+            "l2_policy": "inputs larger than L2: per-GPU state %.0f MB at %d GPUs vs 126 MB L2"
+                         % (1e3 * state_gb / max(args.gpus, 1), max(args.gpus, 1))}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -310,6 +318,8 @@ def run_ours(args):
     sm_mhz = (clocks or {}).get("sm_mhz") or pk.get("sm_max_mhz", 1965.0)
     nsm = torch.cuda.get_device_properties(local).multi_processor_count
     smem_peak = 128.0 * nsm * sm_mhz * 1e6 / 1e9
+    cap = ncu_capture(R)
+    winst = cap["winst_per_attempt"]
     line = {
         "metric": METRIC, "value": value, "unit": "attempts/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -318,24 +328,27 @@ def run_ours(args):
         "e2e": {"value": attempts / e2e_s, "unit": "attempts/s", "h2d_bytes_per_step": h2d / K,
                 "d2h_bytes_per_step": d2h / K, "seconds": e2e_s, "breakdown_s": out["seconds"]},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": "colour_sweep", "achieved": achieved, "peak": pk["hbm_gbs"],
+        "roofline": {"bound": "hbm", "kernel": "colour_sweep_fast", "achieved": achieved, "peak": pk["hbm_gbs"],
                      "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
-                     "traffic": NCU_DRAM_BYTES_PER_SWEEP * K / launches / world,
+                     "traffic": cap["traffic_over_algorithmic"] * B_ALG_HBM * per_launch_attempts,
+                     "traffic_source": cap["source"],
                      "peak_source": pk_kind, "bytes_per_attempt": B_ALG_HBM,
                      "note": "instruction-issue-bound kernel (~6 thread-instructions per attempt, no contraction): "
                              "the HBM fraction is low by construction, traffic (ncu, bytes per launch) equals the "
                              "algorithmic bytes; see roofline_issue and DESIGN.md section 4"},
-        "roofline_issue": {"bound": "issue_slots", "achieved": NCU_WINST_PER_ATTEMPT * value / world / 1e9,
+        "roofline_issue": {"bound": "issue_slots", "achieved": winst * value / world / 1e9,
                            "peak": nsm * 4 * sm_mhz * 1e6 / 1e9, "unit": "G warp-inst/s",
-                           "frac": NCU_WINST_PER_ATTEMPT * value / world / (nsm * 4 * sm_mhz * 1e6),
+                           "frac": winst * value / world / (nsm * 4 * sm_mhz * 1e6),
                            "peak_source": "%d SMs x 4 schedulers x 1 warp-inst/clk x %.0f MHz" % (nsm, sm_mhz),
-                           "warp_inst_per_attempt": NCU_WINST_PER_ATTEMPT,
-                           "note": "what binds this kernel: ncu shows 75% of the issue slots used, ALU pipe 63%"},
+                           "warp_inst_per_attempt": winst, "warp_inst_source": cap["source"],
+                           "note": "what binds this kernel with many rows per GPU (ncu: 75% of the issue slots used at "
+                                   "4096 rows, ALU pipe 63%); with 512 rows per GPU the dependency chain of the "
+                                   "natural-order wavefront binds it (53% of the slots)"},
         "roofline_smem": {"achieved": B_ALG_SMEM * value / world / 1e9, "peak": smem_peak, "unit": "GB/s",
                           "frac": B_ALG_SMEM * value / world / 1e9 / smem_peak,
                           "bytes_per_attempt": B_ALG_SMEM, "peak_source": "128 B/clk/SM x %d SMs x %.0f MHz" % (nsm, sm_mhz)},
         "gather_ms": gather_ms,
-        "residual_energy_per_spin": {"mean_over_slices": float(en.mean() / n), "best_slice_mean": float(en.min(axis=1).mean() / n)},
+        "energy_per_spin": {"mean_over_slices": float(en.mean() / n), "best_slice_mean": float(en.min(axis=1).mean() / n)},
     }
     # ---- CPU baseline on this box's host cores (bounded sample), rank 0, N=1 only
     if world == 1 and not args.no_cpu:

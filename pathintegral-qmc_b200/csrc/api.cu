@@ -799,6 +799,26 @@ int piqmc_set_graph(piqmc_handle h, int nspins, int maxnb, const int32_t *idx, c
         PIQMC_REQUIRE(idx[e] >= 0 && idx[e] < nspins, PIQMC_EINVAL,
                       "neighbour index %d out of range at entry %zu", idx[e], e);
     if (color) TRY(check_colouring(nspins, maxnb, idx, J, ncolors, color));
+    // every bond must appear in the rows of both its spins with the same coupling, as tools.GenerateNeighbors
+    // lists it (piqmc/tools.pyx:74-96): the sweeps read row i for spin i, the energy reduction counts a bond
+    // in the row of its smaller index
+    {
+        std::vector<int> pending;
+        for (int i = 0; i < nspins; i++)
+            for (int n = 0; n < maxnb; n++) {
+                const size_t e = (size_t)i * maxnb + n;
+                const int j = idx[e];
+                if (j == i || J[e] == 0.0) continue;
+                int listed = 0, listed_back = 0;
+                for (int m = 0; m < maxnb; m++) {
+                    if (idx[(size_t)i * maxnb + m] == j && J[(size_t)i * maxnb + m] == J[e]) listed++;
+                    if (idx[(size_t)j * maxnb + m] == i && J[(size_t)j * maxnb + m] == J[e]) listed_back++;
+                }
+                PIQMC_REQUIRE(listed == listed_back, PIQMC_EINVAL,
+                              "neighbour table is not symmetric: the bond (%d, %d) with J = %g is listed %d time(s) in "
+                              "row %d and %d time(s) in row %d", i, j, J[e], listed, i, listed_back, j);
+            }
+    }
     PIQMC_CUDA(cudaStreamSynchronize(h->stream));
     const int old_nspins = h->nspins;
     free_graph(h);

@@ -29,9 +29,9 @@ __device__ __forceinline__ float flip_sign(float negJ2, uint32_t bit)
 
 // the uniform of (row, lane, spin, sweep): Philox block (spin, lane>>2, sweep, row), word lane&3
 __device__ __forceinline__ uint32_t lane_uniform(int lane, uint32_t spin, uint32_t sweep, uint32_t prow,
-                                                 uint32_t k0, uint32_t k1)
+                                                 uint32_t k0, uint32_t k1, uint32_t stream)
 {
-    const u32x4 r = philox4x32_10(spin, (uint32_t)(lane >> 2) | (PIQMC_STREAM_SWEEP << 16), sweep, prow, k0, k1);
+    const u32x4 r = philox4x32_10(spin, (uint32_t)(lane >> 2) | (stream << 16), sweep, prow, k0, k1);
     const int q = lane & 3;
     return q == 0 ? r.x : (q == 1 ? r.y : (q == 2 ? r.z : r.w));
 }
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(128) colour_sweep_generic(
                 if (!acc) {
                     const float x = __fmul_rn(ee, invT);
                     if (x >= PIQMC_XCUT)
-                        acc = lane_uniform(k, (uint32_t)i, sweep, prow, k0, k1) < colour_thresh(x);
+                        acc = lane_uniform(k, (uint32_t)i, sweep, prow, k0, k1, QA ? PIQMC_STREAM_SWEEP : PIQMC_STREAM_SA) < colour_thresh(x);
                 }
                 if (acc) w ^= (1ull << k);
             }

@@ -168,6 +168,7 @@ struct piqmc_ctx {
 #define PIQMC_STREAM_SWEEP 0u
 #define PIQMC_STREAM_INIT 1u
 #define PIQMC_STREAM_GLOBAL 2u
+#define PIQMC_STREAM_SA 3u      // SA sweeps: a pre-anneal and the anneal that follows may share a seed
 #define PIQMC_XCUT (-22.0f)
 
 struct u32x4 {

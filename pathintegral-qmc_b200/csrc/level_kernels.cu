@@ -311,7 +311,7 @@ __device__ __forceinline__ void lv_serve_requests(const LevelArgs &a, const LvRe
             if (need4) {
                 const LvScratch &o = scratch[r.owner >> 5];
                 const int seg = (segS > 1) ? (4 * b) / segP : 0;
-                const u32x4 u = philox4x32_10(o.spin, (uint32_t)(b - seg * (segP >> 2)) | (PIQMC_STREAM_SWEEP << 16), o.sweep,
+                const u32x4 u = philox4x32_10(o.spin, (uint32_t)(b - seg * (segP >> 2)) | ((QA ? PIQMC_STREAM_SWEEP : PIQMC_STREAM_SA) << 16), o.sweep,
                                               o.prow0 + (r.owner & 31u) * (uint32_t)segS + (uint32_t)seg, a.k0, a.k1);
                 const uint32_t *thr = o.thr;
                 const uint64_t zz[4] = {r.z[0], r.z[1], r.z[2], r.z[3]};

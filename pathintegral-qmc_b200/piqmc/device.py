@@ -408,12 +408,8 @@ def pinned_empty(shape, dtype):
     n = int(np.prod(shape)) * dtype.itemsize
     owner = _Pinned(n)
     buf = (ctypes.c_char * max(n, 1)).from_address(owner.ptr.value)
-    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
-    _PINNED[arr.__array_interface__["data"][0]] = owner      # keep alive with the process
-    return arr
-
-
-_PINNED = {}
+    buf._piqmc_owner = owner                                  # the array's base keeps the allocation alive
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
 
 def order_levels(nbs, order=None):

@@ -39,22 +39,35 @@ def gather_rows(local, nreplicas, group=None):
     return torch.cat([out[r, :counts[r]] for r in range(world)], dim=0)
 
 
+def _my_count(nreplicas, group):
+    import torch.distributed as dist
+    return shard_replicas(nreplicas, dist.get_world_size(group), dist.get_rank(group))[1]
+
+
 def gather_energies(dev, nreplicas, group=None):
     """Final-energy gather for a Device whose resident rows are this rank's replica shard:
-    runs the device energy reduction and all-gathers float64[nreplicas, lanes] over NCCL without
-    staging through the host."""
+    runs the device energy reduction and all-gathers float64[nreplicas, slices] over NCCL without
+    staging through the host.  States with several replicas per word (per_word > 1) carry padding
+    replicas in their last word: only this rank's replicas are sent."""
     import torch
     dev.energy(download=False)
     dev.synchronize()
     local = torch.as_tensor(dev.energy_device_array(), device="cuda:%d" % dev.index)
-    return gather_rows(local, nreplicas, group)
+    return gather_rows(local[:_my_count(nreplicas, group)], nreplicas, group)
 
 
 def gather_words(dev, nreplicas, group=None):
-    """Gather of the bit-packed final configurations: uint64[nreplicas, nspins] on every rank."""
+    """Gather of the bit-packed final configurations: uint64[nreplicas, nspins] on every rank (bit k of a
+    word = slice k of that replica, whatever the number of replicas per word on the device)."""
     import torch
     dev.synchronize()
     # device layout is [nspins, nrows]; gather along replicas needs [nrows, nspins].  NCCL has no
     # uint64: reinterpret as int64.
     local = torch.as_tensor(dev.state_device_array(), device="cuda:%d" % dev.index).view(torch.int64)
-    return gather_rows(local.t().contiguous(), nreplicas, group)
+    local = local.t().contiguous()
+    S = dev.per_word
+    if S > 1:                                      # segments of `slices` lanes -> one word per replica
+        P = dev.lanes // S
+        mask = (1 << P) - 1
+        local = torch.stack([(local >> (g * P)) & mask for g in range(S)], dim=1).reshape(-1, local.shape[1])
+    return gather_rows(local[:_my_count(nreplicas, group)].contiguous(), nreplicas, group)

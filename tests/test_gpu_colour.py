@@ -523,3 +523,37 @@ def test_replicas_per_word_bit_exact(dev, P, R, T):
     assert np.array_equal(got, want)
     assert np.array_equal(many["words"], one["words"]) and np.array_equal(up["words"], one["words"])
     assert np.array_equal(many["energies"], one["energies"]) and np.array_equal(up["energies"], one["energies"])
+
+
+def test_path_graph_natural_order_exceeds_one_grid(dev):
+    """A path graph in natural order has N levels and a level gap of 1: the period-major order of the
+    dataflow kernel would need (1 + N/2) * N units -- more than one grid holds at N = 65536.  The call
+    must not truncate the grid silently: it runs class by class and still equals the sequential sweep."""
+    n, R, P = 65536, 3, 8
+    rng = np.random.RandomState(5)
+    nbs = np.zeros((n, 2, 2))
+    Jb = rng.randn(n - 1)
+    for i in range(n - 1):
+        nbs[i, 1] = (i + 1, Jb[i])
+        nbs[i + 1, 0] = (i, Jb[i])
+    nbs[0, 0] = (0, 0.0)
+    nbs[n - 1, 1] = (n - 1, 0.0)
+    idx, J32 = O.nbs_to_ell(nbs)
+    color = tools.OrderLevels(nbs)
+    assert color.max() == n - 1
+    sched = np.array([0.7])
+    init = O.colour_init_spins(3, 0, R, n)
+    want = np.repeat(init[:, :, None], P, axis=2).copy()
+    O.qa_colour(sched, 1, P, 0.3, idx, J32, color, want, 3, 0, 0, 0)
+    dev.set_graph(nbs, color)
+    dev.set_variant(2)
+    try:
+        dev.state_alloc(R, P)
+        dev.state_init_random(3, 0, tile=True)
+        l0 = dev.launch_count
+        dev.qa_colour(sched, 1, 0.3, 3)
+        assert dev.launch_count - l0 == n                      # one launch per class
+        got = np.transpose(tools.UnpackWords(dev.state_download_words(), P), (0, 2, 1))
+    finally:
+        dev.set_variant(0)
+    assert np.array_equal(want, got)

@@ -81,3 +81,44 @@ def test_gloo_sharded_anneal_equals_unsharded(tmp_path, world, R):
     words = T.PackWords(np.transpose(spins, (0, 2, 1))).astype(np.int64)
     assert np.array_equal(np.load(tmp_path / "w.npy"), words)
     np.testing.assert_allclose(np.load(tmp_path / "en.npy"), en, rtol=0, atol=0)
+
+
+def _gpu_worker(rank, world, port, R, out_dir):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, "pathintegral-qmc_b200"), os.path.join(root, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(0)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", 0))
+    import piqmc.qmc as qmc
+    import piqmc.tools as T
+    from piqmc import device
+    from piqmc.shard import gather_energies, gather_words
+    nbs, color = T.GaussianTorusNeighbors(8, 5)
+    dev = device.Device(0)
+    sched = np.linspace(1.5, 1e-8, 5)
+    out = {}
+    for S in (1, 3):                                 # one replica per word, then three (P = 20)
+        qmc.QuantumAnnealReplicas(sched, 1, 20, 0.05, 64, None, nbs, 77, color=color, nreplicas=R, device=dev,
+                                  per_word=S, energies=False, download=False)
+        out[S] = (gather_energies(dev, R).cpu().numpy(), gather_words(dev, R).cpu().numpy())
+    np.save(os.path.join(out_dir, "en1.npy"), out[1][0])
+    np.save(os.path.join(out_dir, "en3.npy"), out[3][0])
+    np.save(os.path.join(out_dir, "w1.npy"), out[1][1])
+    np.save(os.path.join(out_dir, "w3.npy"), out[3][1])
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_gather_of_states_with_several_replicas_per_word(tmp_path):
+    """gather_energies / gather_words on a state with three replicas per word (P = 20; 100 replicas do not fill
+    the last word) give, replica by replica, what the one-replica-per-word state gives."""
+    R = 100
+    mp.spawn(_gpu_worker, args=(1, _free_port(), R, str(tmp_path)), nprocs=1, join=True)
+    en1, en3 = np.load(tmp_path / "en1.npy"), np.load(tmp_path / "en3.npy")
+    w1, w3 = np.load(tmp_path / "w1.npy"), np.load(tmp_path / "w3.npy")
+    assert en1.shape == (R, 20) and w1.shape == (R, 64)
+    assert np.array_equal(en1, en3) and np.array_equal(w1, w3)
