@@ -355,6 +355,18 @@ static bool level_selected(const piqmc_ctx *h, int qa, int trotter)
     return e && atoi(e) != 0;
 }
 
+// The resident kernel runs any graph whose per-row state fits in shared memory (one replica per word, no
+// world-line moves).  Chosen for graphs the table kernels cannot run (maxnb > 4) and for tiny graphs, whose
+// colour classes are too small for anything that synchronises between classes.
+static bool resident_selected(const piqmc_ctx *h, int qa)
+{
+    if (h->global_moves || h->seg_S != 1 || !h->d_words || resident_rows_per_block(h, qa) == 0) return false;
+    if (h->variant == 5) return true;
+    if (h->variant != 0) return false;
+    if (const char *e = getenv("PIQMC_RESIDENT")) return atoi(e) != 0;
+    return h->maxnb > 4 || h->nspins <= 64;
+}
+
 static int apply_colouring(piqmc_ctx *h, int ncolors, const int32_t *color, bool validate)
 {
     if (validate) {
@@ -509,8 +521,9 @@ static int run_colour_sweeps(piqmc_ctx *h, int qa, int trotter, int nsched, int 
     if (nsweeps == 0) return PIQMC_OK;
     // static colourings with many levels and a small level gap (a path graph in natural order) would need
     // more units than one grid holds: those run class by class (or through the chain pipeline below)
-    const bool use_level = level_selected(h, qa, trotter);
-    const bool fast = !use_level && piqmc_fast_ok(h, qa, trotter) && (orders || launch_fast_fits(h, h->flow_extra));
+    const bool resident = resident_selected(h, qa);
+    const bool use_level = !resident && level_selected(h, qa, trotter);
+    const bool fast = !resident && !use_level && piqmc_fast_ok(h, qa, trotter) && (orders || launch_fast_fits(h, h->flow_extra));
     if (!orders) PIQMC_REQUIRE(h->ncolors > 0, PIQMC_ENOGRAPH, "graph has no colouring");
     else TRY(check_orders(N, nsweeps, orders));
     if (!orders && use_level)
@@ -519,7 +532,7 @@ static int run_colour_sweeps(piqmc_ctx *h, int qa, int trotter, int nsched, int 
 
     // per-sweep parameters (fast path)
     DevBuf<float> d_jp2, d_invT;
-    if (fast) {
+    if (fast || resident) {
         std::vector<float> a(nsweeps), b(nsweeps);
         for (size_t s = 0; s < nsweeps; s++) {
             a[s] = jp2[s / mcsteps];
@@ -532,7 +545,26 @@ static int run_colour_sweeps(piqmc_ctx *h, int qa, int trotter, int nsched, int 
         PIQMC_CUDA(cudaStreamSynchronize(h->stream));     // a, b are about to go out of scope
     }
 
-    if (!orders && chain_selected(h, qa, trotter))
+    if (resident) {
+        // sequential sweeps in shared memory: the classes in ascending order, or the visiting orders themselves
+        if (!orders) {
+            TRY(launch_resident_sweeps(h, qa, trotter, h->d_members, 0, (int)nsweeps, d_jp2.p, d_invT.p, seed, row0, sweep0));
+            PIQMC_CUDA(cudaStreamSynchronize(h->stream));    // the per-sweep parameter arrays must outlive the launch
+            return PIQMC_OK;
+        }
+        const size_t chunk = std::max<size_t>(1, std::min<size_t>(nsweeps, (size_t)(64u << 20) / ((size_t)N * 4)));
+        DevBuf<int32_t> d_ord;
+        PIQMC_CUDA(d_ord.alloc(chunk * N));
+        for (size_t base = 0; base < nsweeps; base += chunk) {
+            const size_t m = std::min(chunk, nsweeps - base);
+            PIQMC_CUDA(cudaMemcpyAsync(d_ord.p, orders + base * N, m * N * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+            TRY(launch_resident_sweeps(h, qa, trotter, d_ord.p, 1, (int)m, d_jp2.p + base, d_invT.p + base, seed, row0,
+                                       sweep0 + (uint32_t)base));
+            PIQMC_CUDA(cudaStreamSynchronize(h->stream));    // the orders are reused or freed next
+        }
+        return PIQMC_OK;
+    }
+    if (!orders && !use_level && chain_selected(h, qa, trotter))
         return launch_chain_sweeps(h, qa, nsched, mcsteps, jp2.data(), invT.data(), seed, row0, sweep0);
     if (!orders) {
         if (fast) {
@@ -1090,7 +1122,7 @@ int piqmc_state_alloc_packed(piqmc_handle h, int nrows, int slices, int per_word
 {
     USE(h);
     PIQMC_REQUIRE(h->nspins > 0, PIQMC_ENOGRAPH, "piqmc_set_graph has not been called");
-    PIQMC_REQUIRE(nrows > 0 && nrows <= 65535, PIQMC_EINVAL, "nrows must be in [1, 65535]");
+    PIQMC_REQUIRE(nrows > 0 && nrows <= (1 << 24), PIQMC_EINVAL, "nrows must be in [1, 2^24]");
     PIQMC_REQUIRE(slices >= 1 && slices <= 64, PIQMC_EINVAL,
                   "lanes must be in [1, 64] (the packed path holds all slices of a spin in one 64-bit word)");
     TRY(check_packing(slices, per_word));
@@ -1127,7 +1159,7 @@ int piqmc_state_replicas_to_slices_packed(piqmc_handle h, int nreplicas, int sli
     PIQMC_REQUIRE(slices >= 2 && slices <= 64, PIQMC_EINVAL, "slices must be in [2, 64]");
     TRY(check_packing(slices, per_word));
     const int dst_rows = (nreplicas + per_word - 1) / per_word;
-    PIQMC_REQUIRE(dst_rows <= 65535, PIQMC_EINVAL, "too many rows");
+    PIQMC_REQUIRE(dst_rows <= (1 << 24), PIQMC_EINVAL, "too many rows");
     uint64_t *src = h->d_words;
     const int src_rows = h->nrows;
     uint64_t *dst = nullptr;
@@ -1215,7 +1247,7 @@ int piqmc_set_global_moves(piqmc_handle h, int enable)
 
 int piqmc_set_variant(piqmc_handle h, int variant)
 {
-    PIQMC_REQUIRE(h != nullptr && variant >= 0 && variant <= 4, PIQMC_EINVAL, "variant must be 0 ... 4");
+    PIQMC_REQUIRE(h != nullptr && variant >= 0 && variant <= 5, PIQMC_EINVAL, "variant must be 0 ... 5");
     h->variant = variant;
     return PIQMC_OK;
 }

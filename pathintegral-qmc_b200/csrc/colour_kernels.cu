@@ -107,6 +107,128 @@ __global__ void __launch_bounds__(128) colour_sweep_generic(
     wrow[(size_t)i * nrows] = w;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Resident variant: small graphs.  When the words of all spins of a block's rows fit in shared memory
+// (N * 8 bytes per row), the whole run of sweeps happens there: a row is private to the thread(s) that own
+// it, so the spins are visited one after the other in the sequential order the colouring stands for (the
+// classes in ascending order; or the per-sweep visiting orders themselves) without any barrier, flag or
+// launch in between, and global memory is touched twice -- state in, state out.  Any maxnb.  Per-lane
+// arithmetic of the generic variant (same float sequence, same uniforms).  SPLIT = threads per word: SA
+// words hold 64 independent replicas, 8 threads take 8 lanes each (few rows would otherwise leave the device
+// empty: 65536 SA replicas are 1024 words per spin); QA lanes are coupled and stay with one thread.
+// ------------------------------------------------------------------------------------------
+template <int NL, bool QA, int TROTTER, int SPLIT>
+__global__ void __launch_bounds__(128) resident_sweeps(
+    uint64_t *__restrict__ words, int nspins, int nrows, int maxnb, const int32_t *__restrict__ idx,
+    const float *__restrict__ J32, const int32_t *__restrict__ order, int per_sweep_orders, int nsweeps,
+    const float *__restrict__ jp2s, const float *__restrict__ invTs, int lanes, uint32_t k0, uint32_t k1,
+    uint32_t row0, uint32_t sweep0)
+{
+    extern __shared__ __align__(16) unsigned char rs_smem[];
+    const int B = (int)blockDim.x / SPLIT;                         // rows of this block
+    uint64_t *st = reinterpret_cast<uint64_t *>(rs_smem);          // [nspins][B]
+    int32_t *sidx = reinterpret_cast<int32_t *>(st + (size_t)nspins * B);   // [nspins][maxnb]
+    float *snj2 = reinterpret_cast<float *>(sidx + (size_t)nspins * maxnb); // -2 J
+    const int r = (int)threadIdx.x / SPLIT, part = (int)threadIdx.x % SPLIT;
+    const int row = (int)blockIdx.x * B + r;
+    const bool live = row < nrows;
+    for (int i = part; i < nspins; i += SPLIT) st[(size_t)i * B + r] = live ? words[(size_t)i * nrows + row] : 0ull;
+    for (int e = (int)threadIdx.x; e < nspins * maxnb; e += (int)blockDim.x) {
+        sidx[e] = idx[e];
+        snj2[e] = -2.0f * J32[e];
+    }
+    __syncthreads();
+    const unsigned amask = __ballot_sync(0xffffffffu, live);       // the threads of a word stay or leave together
+    if (!live) return;
+    const int l0 = part * NL;                                     // first lane of this thread
+    const uint32_t prow = row0 + (uint32_t)row;
+    constexpr uint32_t STREAM = QA ? PIQMC_STREAM_SWEEP : PIQMC_STREAM_SA;
+
+    for (int s = 0; s < nsweeps; s++) {
+        const float invT = invTs[s];
+        const float njp2 = QA ? -jp2s[s] : 0.0f;
+        const uint32_t sweep = sweep0 + (uint32_t)s;
+        const int32_t *ord = order + (per_sweep_orders ? (size_t)s * nspins : 0);
+        for (int t = 0; t < nspins; t++) {
+            const int i = __ldg(ord + t);
+            uint64_t w = st[(size_t)i * B + r];
+            float e[NL];
+#pragma unroll
+            for (int k = 0; k < NL; k++) e[k] = 0.0f;
+            for (int n = 0; n < maxnb; n++) {
+                const int j = sidx[i * maxnb + n];
+                const float negJ2 = snj2[i * maxnb + n];
+                const uint64_t x = ((j == i) ? w : (w ^ st[(size_t)j * B + r])) >> l0;
+#pragma unroll
+                for (int k = 0; k < NL; k++)
+                    e[k] = __fadd_rn(e[k], flip_sign(negJ2, (uint32_t)(x >> k) & 1u));
+            }
+            u32x4 blk[(NL + 3) / 4];                               // Philox blocks of this thread's lanes, on demand
+            uint32_t have = 0u;
+            uint64_t flips = 0ull;                                 // SPLIT > 1: this thread's accepted lanes
+#pragma unroll
+            for (int pass = 0; pass < ((QA && TROTTER == 1) ? 2 : 1); pass++) {
+#pragma unroll
+                for (int k = 0; k < NL; k++) {
+                    if (QA && TROTTER == 1 && (k & 1) != pass) continue;
+                    const int lane = l0 + k;
+                    if (lane < lanes) {
+                        float ee = e[k];
+                        if (QA) {
+                            const uint32_t own = (uint32_t)(w >> lane) & 1u;
+                            int kl, kr;
+                            if (TROTTER == 1) {
+                                kl = (lane == 0) ? lanes - 1 : lane - 1;
+                                kr = (lane == lanes - 1) ? 0 : lane + 1;
+                            } else {
+                                kl = lanes - 1;
+                                kr = 1;
+                            }
+                            const uint32_t bl = (uint32_t)(w >> kl) & 1u;
+                            const uint32_t br = (uint32_t)(w >> kr) & 1u;
+                            const float tsum = __fadd_rn(flip_sign(njp2, own ^ bl), flip_sign(njp2, own ^ br));
+                            ee = __fadd_rn(ee, tsum);
+                        }
+                        ee = __fadd_rn(ee, 0.0f);          // canonical zero (-0 -> +0)
+                        bool acc = QA ? (ee > 0.0f) : (ee >= 0.0f);
+                        if (!acc) {
+                            const float x = __fmul_rn(ee, invT);
+                            if (x >= PIQMC_XCUT) {
+                                const int q = k >> 2;                      // lanes are 4-aligned: block (lane >> 2)
+                                if (!((have >> q) & 1u)) {
+                                    blk[q] = philox4x32_10((uint32_t)i, (uint32_t)(lane >> 2) | (STREAM << 16), sweep, prow, k0, k1);
+                                    have |= 1u << q;
+                                }
+                                const uint32_t u = (k & 3) == 0 ? blk[q].x : ((k & 3) == 1 ? blk[q].y : ((k & 3) == 2 ? blk[q].z : blk[q].w));
+                                acc = u < colour_thresh(x);
+                            }
+                        }
+                        if (acc) {
+                            if (SPLIT == 1) w ^= (1ull << lane);
+                            else flips |= 1ull << lane;
+                        }
+                    }
+                }
+            }
+            if (SPLIT > 1) {                               // lanes are independent (SA): merge the threads' slices
+#pragma unroll
+                for (int d = 1; d < SPLIT; d <<= 1) {
+                    const uint32_t lo = __shfl_xor_sync(amask, (uint32_t)flips, d);
+                    const uint32_t hi = __shfl_xor_sync(amask, (uint32_t)(flips >> 32), d);
+                    flips |= ((uint64_t)hi << 32) | lo;
+                }
+                w ^= flips;                                // (the shuffles: every thread of the word has read its inputs)
+                if (part == 0) st[(size_t)i * B + r] = w;
+                __syncwarp(amask);
+            } else {
+                st[(size_t)i * B + r] = w;
+            }
+        }
+    }
+    for (int i = part; i < nspins; i += SPLIT) words[(size_t)i * nrows + row] = st[(size_t)i * B + r];
+}
+
 // ------------------------------------------------------------------------------------------
 // state initialisation / packing
 // ------------------------------------------------------------------------------------------
@@ -224,6 +346,55 @@ static int launch_generic(piqmc_ctx *c, int qa, int trotter, const int32_t *memb
     c->launches++;
     PIQMC_CUDA(cudaGetLastError());
     return PIQMC_OK;
+}
+
+// rows per block of the resident variant for this graph and state (0: the state does not fit)
+int resident_rows_per_block(const piqmc_ctx *c, int qa)
+{
+    const int split = qa ? 1 : 8;
+    for (int threads = 128; threads >= 32; threads >>= 1) {
+        const int B = threads / split;
+        const size_t smem = (size_t)c->nspins * B * 8 + (size_t)c->nspins * c->maxnb * 8;
+        if (smem <= 160 * 1024) return B;
+    }
+    return 0;
+}
+
+template <int NL, bool QA, int TROTTER, int SPLIT>
+static int launch_resident_t(piqmc_ctx *c, const int32_t *d_order, int per_sweep_orders, int nsweeps,
+                             const float *d_jp2, const float *d_invT, uint64_t seed, uint32_t row0, uint32_t sweep0)
+{
+    const int B = resident_rows_per_block(c, QA);
+    const size_t smem = (size_t)c->nspins * B * 8 + (size_t)c->nspins * c->maxnb * 8;
+    auto kern = resident_sweeps<NL, QA, TROTTER, SPLIT>;
+    PIQMC_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)((c->nrows + B - 1) / B), B * SPLIT, smem, c->stream>>>(
+        c->d_words, c->nspins, c->nrows, c->maxnb, c->d_idx, c->d_J32, d_order, per_sweep_orders, nsweeps, d_jp2, d_invT,
+        c->lanes, (uint32_t)seed, (uint32_t)(seed >> 32), row0, sweep0);
+    c->launches++;
+    PIQMC_CUDA(cudaGetLastError());
+    return PIQMC_OK;
+}
+
+// nsweeps sweeps, each the sequential sweep in d_order (one list, or one per sweep), state resident in shared memory
+int launch_resident_sweeps(piqmc_ctx *c, int qa, int trotter, const int32_t *d_order, int per_sweep_orders, int nsweeps,
+                           const float *d_jp2, const float *d_invT, uint64_t seed, uint32_t row0, uint32_t sweep0)
+{
+    if (nsweeps <= 0) return PIQMC_OK;
+    PIQMC_REQUIRE(resident_rows_per_block(c, qa) > 0, PIQMC_EINVAL, "the state of one row does not fit in shared memory");
+#define RS_ARGS c, d_order, per_sweep_orders, nsweeps, d_jp2, d_invT, seed, row0, sweep0
+    if (!qa) return launch_resident_t<8, false, 0, 8>(RS_ARGS);
+    if (trotter == 1) {
+        if (c->lanes <= 8) return launch_resident_t<8, true, 1, 1>(RS_ARGS);
+        if (c->lanes <= 16) return launch_resident_t<16, true, 1, 1>(RS_ARGS);
+        if (c->lanes <= 32) return launch_resident_t<32, true, 1, 1>(RS_ARGS);
+        return launch_resident_t<64, true, 1, 1>(RS_ARGS);
+    }
+    if (c->lanes <= 8) return launch_resident_t<8, true, 0, 1>(RS_ARGS);
+    if (c->lanes <= 16) return launch_resident_t<16, true, 0, 1>(RS_ARGS);
+    if (c->lanes <= 32) return launch_resident_t<32, true, 0, 1>(RS_ARGS);
+    return launch_resident_t<64, true, 0, 1>(RS_ARGS);
+#undef RS_ARGS
 }
 
 int launch_colour_sweep(piqmc_ctx *c, int qa, int trotter, const int32_t *members, int nmem, float jp2,

@@ -232,6 +232,10 @@ int launch_replicas_to_slices(piqmc_ctx *c, const uint64_t *d_src, int src_rows,
 // one colour class (device list `members`) of one sweep; qa != 0: QA rules (jp2 = 2*jperp)
 int launch_colour_sweep(piqmc_ctx *c, int qa, int trotter, const int32_t *members, int nmem, float jp2,
                         float invT, uint64_t seed, uint32_t row0, uint32_t sweep);
+// small graphs: the whole run of sweeps with the state resident in shared memory (colour_kernels.cu)
+int launch_resident_sweeps(piqmc_ctx *c, int qa, int trotter, const int32_t *d_order, int per_sweep_orders, int nsweeps,
+                           const float *d_jp2, const float *d_invT, uint64_t seed, uint32_t row0, uint32_t sweep0);
+int resident_rows_per_block(const piqmc_ctx *c, int qa);
 int launch_energy(piqmc_ctx *c);
 int launch_energy_coo(piqmc_ctx *c, int nspins, int nnz, const int32_t *d_row, const int32_t *d_col,
                       const double *d_val, int nconfs, const int8_t *d_spins, double *d_out);
@@ -273,8 +277,8 @@ int piqmc_grow(T *&p, size_t &have, size_t want, cudaStream_t stream)
 // launch geometry of the chain pipeline for the current plan and state; false: it cannot run them
 bool chain_geometry(const piqmc_ctx *c, int qa, ChainGeom *g);
 // variant: 0 auto, 1 generic, 2 dataflow kernel whenever the graph qualifies, 3 chain pipeline whenever there
-// is a plan, else as 2, 4 level-synchronous kernel whenever the graph qualifies, else as 2 (2, 3, 4: used by
-// the parity tests)
+// is a plan, else as 2, 4 level-synchronous kernel whenever the graph qualifies, else as 2, 5 resident kernel
+// whenever the state of a row fits in shared memory, else as 0 (2 ... 5: used by the parity tests)
 static inline bool piqmc_fast_ok(const piqmc_ctx *c, int qa, int trotter)
 {
     (void)qa;

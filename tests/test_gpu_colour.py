@@ -67,7 +67,7 @@ QA_CASES = [
 ]
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 5])
 @pytest.mark.parametrize("inst,P,T,sch,mcsteps,R", QA_CASES)
 def test_qa_colour_bit_exact(golden, dev, inst, P, T, sch, mcsteps, R, variant):
     nbs, idx, J32, color = _graph(golden, inst)
@@ -103,6 +103,36 @@ def test_qa_colour_periodic_trotter(golden, dev, variant):
         assert np.array_equal(want, got)
 
 
+@pytest.mark.parametrize("inst", ["boixo16", "hopfield8"])
+def test_resident_kernel_periodic_trotter_and_orders(golden, dev, inst):
+    """The resident kernel (state of a row in shared memory, sequential visits): periodic Trotter neighbours
+    with even and odd slice counts, and per-sweep visiting orders (the orders themselves are the sweep)."""
+    nbs, idx, J32, color = _graph(golden, inst)
+    n = NSPINS[inst]
+    sched = np.linspace(2.0, 1e-8, 6)
+    for P in (12, 7, 64):
+        want, got = _qa_both(dev, nbs, idx, J32, color, sched, 2, P, 0.3, 37, seed=5 + P, trotter=1, variant=5)
+        assert np.array_equal(want, got)
+    prng = np.random.RandomState(3)
+    orders = np.stack([prng.permutation(n) for _ in range(12)]).astype(np.int32)
+    R, P = 45, 10
+    init = O.colour_init_spins(8, 2, R, n)
+    want = np.repeat(init[:, :, None], P, axis=2).copy()
+    O.qa_colour(sched, 2, P, 0.3, idx, J32, color, want, 8, replica0=2, sweep0=4, orders=orders)
+    dev.set_graph(nbs, color)
+    dev.set_variant(5)
+    try:
+        dev.state_alloc(R, P)
+        dev.state_init_random(8, 2, tile=True)
+        l0 = dev.launch_count
+        dev.qa_colour(sched, 2, 0.3, 8, replica0=2, sweep0=4, orders=orders)
+        assert dev.launch_count - l0 == 1                      # the whole run: one launch
+        got = np.transpose(tools.UnpackWords(dev.state_download_words(), P), (0, 2, 1))
+    finally:
+        dev.set_variant(0)
+    assert np.array_equal(want, got)
+
+
 def test_qa_colour_sharding_invariance(dev):
     """Replicas [0,8) in one state == replicas [0,3) and [3,8) run separately with replica0."""
     import piqmc.qmc as qmc
@@ -116,9 +146,10 @@ def test_qa_colour_sharding_invariance(dev):
     assert np.array_equal(full["energies"], np.concatenate([a["energies"], b["energies"]]))
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 5])
 @pytest.mark.parametrize("inst,sch,mcsteps,R", [
     ("boixo", (1.0, 0.01, 10), 3, 70),
+    ("boixo16", (2.0, 0.5, 6), 2, 1000),                        # hot: most lanes draw
     ("bipartite8", (3.0, 0.01, 10), 2, 64),
     ("hopfield8", (8.0, 1e-8, 5), 10, 130),
     ("inst_0_32x32", (3.0, 0.01, 12), 1, 130),
