@@ -50,6 +50,8 @@ void free_graph(piqmc_ctx *c)
     free_dev(c->d_done);
     free_dev(c->d_cstat);
     free_dev(c->d_lstat);
+    free_dev(c->d_iw);
+    c->int_unit = 0.0f;
     free_dev(c->d_lvoff);
     free_dev(c->d_xrecs);
     free_dev(c->d_stream);
@@ -546,22 +548,33 @@ static int run_colour_sweeps(piqmc_ctx *h, int qa, int trotter, int nsched, int 
     }
 
     if (resident) {
-        // sequential sweeps in shared memory: the classes in ascending order, or the visiting orders themselves
-        if (!orders) {
-            TRY(launch_resident_sweeps(h, qa, trotter, h->d_members, 0, (int)nsweeps, d_jp2.p, d_invT.p, seed, row0, sweep0));
-            PIQMC_CUDA(cudaStreamSynchronize(h->stream));    // the per-sweep parameter arrays must outlive the launch
-            return PIQMC_OK;
+        // sequential sweeps in shared memory: the classes in ascending order, or the visiting orders themselves.
+        // Integer couplings: the bit-sliced kernel takes the sweeps that are cold enough for it (few lanes need
+        // a uniform: T <= unit / 2; it visits those lanes one by one) -- with a falling schedule the hot head of
+        // the run goes through the per-lane kernel; SA words are not split over threads there, so it also needs
+        // enough rows to fill the device.
+        size_t cold_from = nsweeps;
+        if (resident_int_ok(h, qa, trotter) && (qa || h->nrows >= 4096 || getenv("PIQMC_FORCE_INT_KERNEL"))) {
+            cold_from = 0;
+            if (!getenv("PIQMC_FORCE_INT_KERNEL"))
+                for (size_t s = 0; s < nsweeps; s++)
+                    if (1.0f / invT[s / mcsteps] > 0.5f * h->int_unit) cold_from = s + 1;
         }
-        const size_t chunk = std::max<size_t>(1, std::min<size_t>(nsweeps, (size_t)(64u << 20) / ((size_t)N * 4)));
+        const size_t chunk = !orders ? nsweeps
+                                     : std::max<size_t>(1, std::min<size_t>(nsweeps, (size_t)(64u << 20) / ((size_t)N * 4)));
         DevBuf<int32_t> d_ord;
-        PIQMC_CUDA(d_ord.alloc(chunk * N));
-        for (size_t base = 0; base < nsweeps; base += chunk) {
-            const size_t m = std::min(chunk, nsweeps - base);
-            PIQMC_CUDA(cudaMemcpyAsync(d_ord.p, orders + base * N, m * N * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-            TRY(launch_resident_sweeps(h, qa, trotter, d_ord.p, 1, (int)m, d_jp2.p + base, d_invT.p + base, seed, row0,
-                                       sweep0 + (uint32_t)base));
-            PIQMC_CUDA(cudaStreamSynchronize(h->stream));    // the orders are reused or freed next
+        if (orders) PIQMC_CUDA(d_ord.alloc(chunk * N));
+        for (size_t base = 0; base < nsweeps;) {
+            size_t m = std::min(chunk, nsweeps - base);
+            if (base < cold_from) m = std::min(m, cold_from - base);          // a segment is hot or cold, not both
+            if (orders)
+                PIQMC_CUDA(cudaMemcpyAsync(d_ord.p, orders + base * N, m * N * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+            TRY(launch_resident_sweeps(h, qa, trotter, orders ? d_ord.p : h->d_members, orders ? 1 : 0, (int)m, d_jp2.p + base,
+                                       d_invT.p + base, seed, row0, sweep0 + (uint32_t)base, base >= cold_from ? 1 : 0));
+            if (orders) PIQMC_CUDA(cudaStreamSynchronize(h->stream));         // the orders are reused or freed next
+            base += m;
         }
+        PIQMC_CUDA(cudaStreamSynchronize(h->stream));        // the per-sweep parameter arrays must outlive the launches
         return PIQMC_OK;
     }
     if (!orders && !use_level && chain_selected(h, qa, trotter))
@@ -888,6 +901,47 @@ int piqmc_set_graph(piqmc_handle h, int nspins, int maxnb, const int32_t *idx, c
     PIQMC_CUDA(cudaMalloc(&h->d_level, (size_t)nspins * sizeof(int32_t)));
     PIQMC_CUDA(cudaMalloc(&h->d_recs, (size_t)nspins * sizeof(PiqmcUnitRec)));
     TRY(upload_level_stat(h));
+    // integer couplings: the largest power of two q <= the smallest |J| such that every J32 is an integer
+    // multiple of q with |multiple| <= 7 and row sums of at most 31 (bit-sliced resident kernel)
+    {
+        float amin = 0.0f;
+        for (size_t e = 0; e < ne; e++)
+            if (j32[e] != 0.0f && (amin == 0.0f || fabsf(j32[e]) < amin)) amin = fabsf(j32[e]);
+        float q = 0.0f;
+        if (amin > 0.0f && maxnb <= 8) {
+            int ex = 0;
+            frexpf(amin, &ex);
+            q = ldexpf(1.0f, ex - 1);                              // 2^floor(log2(amin))
+            for (int tries = 0; tries < 3 && q > 0.0f; tries++, q *= 0.5f) {
+                bool ok = true;
+                for (int i = 0; i < nspins && ok; i++) {
+                    int rowsum = 0;
+                    for (int n = 0; n < maxnb && ok; n++) {
+                        const float m = j32[(size_t)i * maxnb + n] / q;
+                        if (m != rintf(m) || fabsf(m) > 7.0f) ok = false;
+                        rowsum += (int)fabsf(m);
+                    }
+                    if (rowsum > 31) ok = false;
+                }
+                if (ok) break;
+                if (tries == 2) q = 0.0f;
+            }
+        }
+        if (q > 0.0f) {
+            bool ok = true;
+            std::vector<int8_t> iw(ne);
+            for (size_t e = 0; e < ne && ok; e++) {
+                const float m = j32[e] / q;
+                ok = m == rintf(m) && fabsf(m) <= 7.0f;
+                iw[e] = (int8_t)m;
+            }
+            if (ok) {
+                PIQMC_CUDA(cudaMalloc(&h->d_iw, ne));
+                PIQMC_CUDA(cudaMemcpy(h->d_iw, iw.data(), ne, cudaMemcpyHostToDevice));
+                h->int_unit = q;
+            }
+        }
+    }
     if (color) TRY(apply_colouring(h, ncolors, color, false));
     // a resident state stays valid for a new graph on the same spins (words are [spin][row],
     // whatever the couplings): the SA pre-anneal -> PIQMC hand-over may change the colouring

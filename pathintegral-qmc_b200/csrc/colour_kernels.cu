@@ -230,6 +230,169 @@ __global__ void __launch_bounds__(128) resident_sweeps(
 }
 
 // ------------------------------------------------------------------------------------------
+// Resident variant for INTEGER couplings (the multispin-coded +-J kernel of BASELINE.json configs[3];
+// piqmc/sa.pyx:339-382 XORs bit-packed replicas and then walks the 64 lanes one by one): when every
+// coupling and field of the graph is a small integer multiple of a power of two q, the in-slice energy
+// difference of a lane is 2q (2n - W) with n = sum of the weights of the columns the lane disagrees with
+// (after flipping the columns with negative coupling) -- every partial sum of the specification's float32
+// sequence is exact, so the order does not matter.  n is accumulated for all 64 lanes at once in five bit
+// planes (ripple-carry adders on 64-bit words); the decisions "accept by sign" / "needs a uniform" are
+// monotone in n, so per Trotter class they are two comparisons of the bit-sliced n with thresholds that
+// the warp works out once per (sweep, spin) -- lane n of the warp evaluates the specification's float32
+// expressions for n -- and only the lanes that need a uniform are visited one by one.
+// QA with the reference's Trotter neighbours, or SA; one replica per word (QA) / 64 replicas per word (SA).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t ge_const(const uint64_t (&b)[5], uint32_t theta)
+{
+    // [n >= theta] for the bit-sliced n (theta <= 32: 32 and more is never reached)
+    if (theta >= 32u) return 0ull;
+    uint64_t ge = ~0ull;
+#pragma unroll
+    for (int p = 0; p < 5; p++) ge = ((theta >> p) & 1u) ? (b[p] & ge) : (b[p] | ge);   // theta is warp-uniform
+    return ge;
+}
+
+template <bool QA>
+__global__ void __launch_bounds__(128) resident_sweeps_int(
+    uint64_t *__restrict__ words, int nspins, int nrows, int maxnb, const int32_t *__restrict__ idx,
+    const int8_t *__restrict__ iw, float unit, const int32_t *__restrict__ order, int per_sweep_orders, int nsweeps,
+    const float *__restrict__ jp2s, const float *__restrict__ invTs, int lanes, uint32_t k0, uint32_t k1,
+    uint32_t row0, uint32_t sweep0)
+{
+    extern __shared__ __align__(16) unsigned char rs_smem[];
+    const int B = (int)blockDim.x;
+    uint64_t *st = reinterpret_cast<uint64_t *>(rs_smem);          // [nspins][B]
+    int32_t *sidx = reinterpret_cast<int32_t *>(st + (size_t)nspins * B);   // [nspins][maxnb]
+    int8_t *sw = reinterpret_cast<int8_t *>(sidx + (size_t)nspins * maxnb); // signed weights
+    __shared__ uint32_t thrtab[4][3][32];                          // per warp: threshold of (class, n)
+    const int r = (int)threadIdx.x, lane = r & 31, warp = r >> 5;
+    const int row = (int)blockIdx.x * B + r;
+    const bool live = row < nrows;                                 // dead rows keep going: the warp needs its lanes
+    for (int i = 0; i < nspins; i++) st[(size_t)i * B + r] = live ? words[(size_t)i * nrows + row] : 0ull;
+    for (int e = r; e < nspins * maxnb; e += B) {
+        sidx[e] = idx[e];
+        sw[e] = iw[e];
+    }
+    __syncthreads();
+    const uint32_t prow = row0 + (uint32_t)row;
+    constexpr uint32_t STREAM = QA ? PIQMC_STREAM_SWEEP : PIQMC_STREAM_SA;
+    constexpr int NC = QA ? 3 : 1;
+    const uint64_t valid = (lanes >= 64) ? ~0ull : ((1ull << lanes) - 1ull);
+    const uint64_t top = 1ull << (lanes - 1);
+    uint32_t(*thr)[32] = thrtab[warp];
+
+    for (int s = 0; s < nsweeps; s++) {
+        const float invT = invTs[s];
+        const float jp2 = QA ? jp2s[s] : 0.0f;
+        const uint32_t sweep = sweep0 + (uint32_t)s;
+        const int32_t *ord = order + (per_sweep_orders ? (size_t)s * nspins : 0);
+        for (int t = 0; t < nspins; t++) {
+            const int i = __ldg(ord + t);
+            const uint64_t w = st[(size_t)i * B + r];
+            // ---- n in bit planes
+            uint64_t b[5] = {0ull, 0ull, 0ull, 0ull, 0ull};
+            int W = 0;
+            for (int n = 0; n < maxnb; n++) {
+                const int wt = sw[i * maxnb + n];                 // warp-uniform
+                if (wt == 0) continue;
+                const int j = sidx[i * maxnb + n];
+                uint64_t z = (j == i) ? w : (w ^ st[(size_t)j * B + r]);
+                if (wt < 0) z = ~z;
+                const int aw = wt < 0 ? -wt : wt;
+                W += aw;
+#pragma unroll
+                for (int jb = 0; jb < 3; jb++)
+                    if ((aw >> jb) & 1) {
+                        uint64_t carry = z;
+#pragma unroll
+                        for (int p = jb; p < 5; p++) {
+                            const uint64_t tt = b[p] & carry;
+                            b[p] ^= carry;
+                            carry = tt;
+                        }
+                    }
+            }
+            // ---- thresholds of n, once per warp: lane n evaluates the specification for n
+            uint32_t tha[NC], thn[NC];
+            {
+                const float e0 = __fmul_rn(2.0f * unit, (float)(2 * lane - W));   // exact
+                __syncwarp();
+#pragma unroll
+                for (int c = 0; c < NC; c++) {
+                    float ee = e0;
+                    if (QA) ee = __fadd_rn(ee, (c == 0) ? -2.0f * jp2 : (c == 1 ? 0.0f : 2.0f * jp2));
+                    ee = __fadd_rn(ee, 0.0f);
+                    const bool acc = QA ? (ee > 0.0f) : (ee >= 0.0f);
+                    const float x = __fmul_rn(ee, invT);
+                    const bool need = !acc && x >= PIQMC_XCUT;
+                    thr[c][lane] = need ? colour_thresh(x) : 0u;
+                    const uint32_t ma = __ballot_sync(0xffffffffu, acc && lane <= W);
+                    const uint32_t mn = __ballot_sync(0xffffffffu, (acc || need) && lane <= W);
+                    tha[c] = ma ? (uint32_t)(__ffs(ma) - 1) : 32u;            // monotone in n: {n >= tha}
+                    thn[c] = mn ? (uint32_t)(__ffs(mn) - 1) : 32u;
+                }
+                __syncwarp();
+            }
+            uint64_t V[3], Nd[3];
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                V[c] = ge_const(b, tha[c]);
+                Nd[c] = (thn[c] < tha[c]) ? (ge_const(b, thn[c]) & ~V[c]) : 0ull;
+            }
+            // one needy lane: its uniform against the threshold of (class, n)
+            u32x4 blk;
+            int blk_q = -1;
+            auto draw = [&](int k, uint32_t c) -> bool {
+                const uint32_t n = (uint32_t)((b[0] >> k) & 1) | (uint32_t)((b[1] >> k) & 1) << 1 | (uint32_t)((b[2] >> k) & 1) << 2 |
+                                   (uint32_t)((b[3] >> k) & 1) << 3 | (uint32_t)((b[4] >> k) & 1) << 4;
+                if (blk_q != (k >> 2)) {
+                    blk = philox4x32_10((uint32_t)i, (uint32_t)(k >> 2) | (STREAM << 16), sweep, prow, k0, k1);
+                    blk_q = k >> 2;
+                }
+                const uint32_t u = (k & 3) == 0 ? blk.x : ((k & 3) == 1 ? blk.y : ((k & 3) == 2 ? blk.z : blk.w));
+                return u < thr[c][n];
+            };
+            uint64_t result;
+            if (!QA) {
+                uint64_t acc = V[0] & valid, need = Nd[0] & valid;
+                while (need) {
+                    const int k = __ffsll((long long)need) - 1;
+                    need &= need - 1;
+                    if (draw(k, 0u)) acc |= 1ull << k;
+                }
+                result = w ^ acc;
+            } else {
+                // the reference's Trotter neighbours: slices P-1 (old value; itself for slice P-1) and 1 (old for
+                // slice 0, itself for slice 1, new for slices >= 2): slice 1 is decided first
+                const uint64_t bl = (w & top) ? ~0ull : 0ull;
+                const uint64_t br_old = (w & 2ull) ? ~0ull : 0ull;
+                const uint64_t XL = (w ^ bl) & ~top;
+                const uint32_t c1 = (uint32_t)(XL >> 1) & 1u;                // right neighbour of slice 1 is itself
+                uint64_t flip1 = 0ull;
+                if ((c1 ? V[1] : V[0]) & 2ull) flip1 = 2ull;
+                else if (((c1 ? Nd[1] : Nd[0]) & 2ull) && draw(1, c1)) flip1 = 2ull;
+                const uint64_t br_new = br_old ^ (flip1 ? ~0ull : 0ull);
+                const uint64_t XR = ((w ^ br_new) & ~1ull) | ((w ^ br_old) & 1ull);   // slice 0 sees the old slice 1
+                const uint64_t todo = valid & ~2ull;
+                const uint64_t C0 = ~(XL | XR), C1 = XL ^ XR, C2 = XL & XR;
+                uint64_t acc = ((C0 & V[0]) | (C1 & V[1]) | (C2 & V[2])) & todo;
+                uint64_t need = ((C0 & Nd[0]) | (C1 & Nd[1]) | (C2 & Nd[2])) & todo;
+                while (need) {
+                    const int k = __ffsll((long long)need) - 1;
+                    need &= need - 1;
+                    const uint32_t c = (uint32_t)((XL >> k) & 1) + (uint32_t)((XR >> k) & 1);
+                    if (draw(k, c)) acc |= 1ull << k;
+                }
+                result = w ^ flip1 ^ acc;
+            }
+            st[(size_t)i * B + r] = result;
+        }
+    }
+    if (live)
+        for (int i = 0; i < nspins; i++) words[(size_t)i * nrows + row] = st[(size_t)i * B + r];
+}
+
+// ------------------------------------------------------------------------------------------
 // state initialisation / packing
 // ------------------------------------------------------------------------------------------
 // all lanes of a segment of P lanes
@@ -376,12 +539,45 @@ static int launch_resident_t(piqmc_ctx *c, const int32_t *d_order, int per_sweep
     return PIQMC_OK;
 }
 
+// the bit-sliced kernel can run this graph and mode (integer couplings; reference Trotter neighbours or SA)
+bool resident_int_ok(const piqmc_ctx *c, int qa, int trotter)
+{
+    return c->int_unit > 0.0f && c->d_iw && !(qa && trotter) && !getenv("PIQMC_NO_INT_KERNEL");
+}
+
+// integer couplings: the bit-sliced kernel
+static int launch_resident_int(piqmc_ctx *c, int qa, const int32_t *d_order, int per_sweep_orders, int nsweeps,
+                               const float *d_jp2, const float *d_invT, uint64_t seed, uint32_t row0, uint32_t sweep0)
+{
+    int B = 128;
+    while (B > 32 && (size_t)c->nspins * B * 8 + (size_t)c->nspins * c->maxnb * 5 > 160 * 1024) B >>= 1;
+    const size_t smem = (size_t)c->nspins * B * 8 + (size_t)c->nspins * c->maxnb * 5;
+    PIQMC_REQUIRE(smem <= 160 * 1024, PIQMC_EINVAL, "the state of one row does not fit in shared memory");
+    if (qa) {
+        PIQMC_CUDA(cudaFuncSetAttribute((const void *)resident_sweeps_int<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        resident_sweeps_int<true><<<(unsigned)((c->nrows + B - 1) / B), B, smem, c->stream>>>(
+            c->d_words, c->nspins, c->nrows, c->maxnb, c->d_idx, c->d_iw, c->int_unit, d_order, per_sweep_orders, nsweeps,
+            d_jp2, d_invT, c->lanes, (uint32_t)seed, (uint32_t)(seed >> 32), row0, sweep0);
+    } else {
+        PIQMC_CUDA(cudaFuncSetAttribute((const void *)resident_sweeps_int<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        resident_sweeps_int<false><<<(unsigned)((c->nrows + B - 1) / B), B, smem, c->stream>>>(
+            c->d_words, c->nspins, c->nrows, c->maxnb, c->d_idx, c->d_iw, c->int_unit, d_order, per_sweep_orders, nsweeps,
+            d_jp2, d_invT, c->lanes, (uint32_t)seed, (uint32_t)(seed >> 32), row0, sweep0);
+    }
+    c->launches++;
+    PIQMC_CUDA(cudaGetLastError());
+    return PIQMC_OK;
+}
+
 // nsweeps sweeps, each the sequential sweep in d_order (one list, or one per sweep), state resident in shared memory
 int launch_resident_sweeps(piqmc_ctx *c, int qa, int trotter, const int32_t *d_order, int per_sweep_orders, int nsweeps,
-                           const float *d_jp2, const float *d_invT, uint64_t seed, uint32_t row0, uint32_t sweep0)
+                           const float *d_jp2, const float *d_invT, uint64_t seed, uint32_t row0, uint32_t sweep0,
+                           int bit_sliced)
 {
     if (nsweeps <= 0) return PIQMC_OK;
     PIQMC_REQUIRE(resident_rows_per_block(c, qa) > 0, PIQMC_EINVAL, "the state of one row does not fit in shared memory");
+    if (bit_sliced && resident_int_ok(c, qa, trotter))
+        return launch_resident_int(c, qa, d_order, per_sweep_orders, nsweeps, d_jp2, d_invT, seed, row0, sweep0);
 #define RS_ARGS c, d_order, per_sweep_orders, nsweeps, d_jp2, d_invT, seed, row0, sweep0
     if (!qa) return launch_resident_t<8, false, 0, 8>(RS_ARGS);
     if (trotter == 1) {

@@ -113,6 +113,9 @@ struct piqmc_ctx {
     std::vector<uint8_t> h_live;    // J != 0 && idx != self
     std::vector<float> h_J32;       // [N][maxnb]
     int32_t *d_level = nullptr;     // colour (level) of every spin (static colouring)
+    // integer couplings (resident bit-sliced kernel): every J = iw * int_unit, |iw| <= 7, row sums <= 31
+    float int_unit = 0.0f;          // 0: the graph does not qualify
+    int8_t *d_iw = nullptr;         // [N][maxnb] signed weights
     PiqmcUnitRec *d_recs = nullptr; // unit records, spins sorted by (level mod D, level): period-major order
     int flow_extra = 0;             // ceil(ncolors / D) - 1 ramp periods
     // dataflow sweep kernel (colour_fast.cu)
@@ -234,7 +237,9 @@ int launch_colour_sweep(piqmc_ctx *c, int qa, int trotter, const int32_t *member
                         float invT, uint64_t seed, uint32_t row0, uint32_t sweep);
 // small graphs: the whole run of sweeps with the state resident in shared memory (colour_kernels.cu)
 int launch_resident_sweeps(piqmc_ctx *c, int qa, int trotter, const int32_t *d_order, int per_sweep_orders, int nsweeps,
-                           const float *d_jp2, const float *d_invT, uint64_t seed, uint32_t row0, uint32_t sweep0);
+                           const float *d_jp2, const float *d_invT, uint64_t seed, uint32_t row0, uint32_t sweep0,
+                           int bit_sliced);
+bool resident_int_ok(const piqmc_ctx *c, int qa, int trotter);
 int resident_rows_per_block(const piqmc_ctx *c, int qa);
 int launch_energy(piqmc_ctx *c);
 int launch_energy_coo(piqmc_ctx *c, int nspins, int nnz, const int32_t *d_row, const int32_t *d_col,

@@ -55,6 +55,32 @@ struct Uniforms {
     }
 };
 
+// exp(x) > u without the exponential where it cannot matter (x <= 0 here, or any x for the multispin
+// variant): below x = -22 the exponential is smaller than 2.79e-10, so every u >= 2.8e-10 rejects -- at the
+// reference's T = 0.01 that is nearly every rejected attempt.  (rand()/RAND_MAX is 0 or >= 4.66e-10.)
+// Exact: the decision is the one the full comparison gives.
+__device__ __forceinline__ bool exp_exceeds(double x, double u)
+{
+    if (x < -22.0 && u >= 2.8e-10) return false;
+    return exp(x) > u;
+}
+
+// The lazy Metropolis test of the sequential variants: exp((double)(ediff / temp)) > rand() / RAND_MAX with
+// ediff <= 0 (piqmc/qmc.pyx:130-133, piqmc/sa.pyx:114-117), consuming one uniform.  With the libc generator
+// the uniform is k / (2^31 - 1) for an integer k: far below the cut (x < -22, nearly every rejected attempt at
+// the reference's T = 0.01) only k == 0 can accept, so neither the double division nor the exponential is
+// evaluated -- the decision is still exactly the one the full expression gives.
+__device__ __forceinline__ bool lazy_accept(Uniforms &us, float ediff, float temp)
+{
+    if (us.table == nullptr) {
+        const int32_t k = us.g.next();
+        us.consumed++;
+        if (temp > 0.0f && ediff < -22.01f * temp) return k == 0 && exp((double)__fdiv_rn(ediff, temp)) > 0.0;
+        return exp((double)__fdiv_rn(ediff, temp)) > (double)k / 2147483647.0;
+    }
+    return exp_exceeds((double)__fdiv_rn(ediff, temp), us.next());
+}
+
 // -(2*jv) with the sign of s_i*s_j applied: the exact value of (-2.0*s_i)*(jv*s_j) for
 // s = +-1 (piqmc/qmc.pyx:111-113).  neg != 0 means s_i*s_j == -1.
 __device__ __forceinline__ float signed_term(float jv, int neg)
@@ -124,8 +150,7 @@ __global__ void __launch_bounds__(32) qa_det_kernel(
                     if (ediff > 0.0f) {
                         flip = true;
                     } else {
-                        const double u = us.next();
-                        flip = exp((double)__fdiv_rn(ediff, temp)) > u;
+                        flip = lazy_accept(us, ediff, temp);
                     }
                     if (flip) row[k] = (int8_t)-own;
                 }
@@ -183,8 +208,7 @@ __global__ void __launch_bounds__(32) sa_det_kernel(
                 if (DENSE ? (ediff > 0.0f) : (ediff >= 0.0f)) {   // >= (sa.pyx:114); dense: > (sa.pyx:180)
                     flip = true;
                 } else {
-                    const double u = us.next();
-                    flip = exp((double)__fdiv_rn(ediff, temp)) > u;
+                    flip = lazy_accept(us, ediff, temp);
                 }
                 if (flip) s[sidx] = (int8_t)-own;
             }
@@ -227,7 +251,7 @@ __global__ void __launch_bounds__(64) sa_multispin_det_kernel(
                     else                   ediff -= 2.0 * jv;
                 }
                 const double u = rands_g[(sweep * nspins + t) * 64 + k];
-                const bool flip = exp(ediff / temp) > u;        // no ediff>0 shortcut (sa.pyx:382)
+                const bool flip = exp_exceeds(ediff / temp, u);     // no ediff>0 shortcut (sa.pyx:382)
                 const uint32_t b = __ballot_sync(0xffffffffu, flip);
                 if ((k & 31) == 0) ballots[k >> 5] = b;
                 __syncthreads();

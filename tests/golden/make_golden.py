@@ -338,6 +338,18 @@ def make_santoro(nrep=256):
     np.savez_compressed(os.path.join(HERE, "ref_santoro.npz"), **out)
 
 
+def make_santoro_long():
+    """The long end of the Santoro protocol (examples/santoro80.py:290-323 sweeps tau upwards): tau = 300 and
+    tau = 1000, fewer replicas (the reference takes 0.4 s and 1.3 s of one core per replica and step count)."""
+    out = {}
+    with mp.Pool(min(8, os.cpu_count()), initializer=_santoro_init) as pool:
+        for tau, nrep in ((300, 256), (1000, 128)):
+            res = np.array(pool.map(_santoro_job, [(r, tau) for r in range(nrep)], chunksize=2))
+            out["qa_par_%d" % tau] = res
+            print("santoro tau", tau, "mean residual/spin", (res.mean() + 10115.3067314770) / 6400.0)
+    np.savez_compressed(os.path.join(HERE, "ref_santoro_long.npz"), **out)
+
+
 def make_config4(nsamples=4096):
     """BASELINE configs[3]: bipartite8 (examples/bipartite8.py:20-27,60-66) and hopfield8
     (examples/hopfield8.py:22-45,98) annealed with the reference's sa.Anneal and
@@ -391,6 +403,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if "--santoro" in sys.argv:
         make_santoro()
+        sys.exit(0)
+    if "--santoro-long" in sys.argv:
+        make_santoro_long()
         sys.exit(0)
     make_vectors()
     if "--dist" in sys.argv:

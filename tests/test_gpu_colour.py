@@ -7,6 +7,8 @@ Two levels (BASELINE.json north_star):
      per-spin-reset variant qmc.QuantumAnneal_parallel (golden distributions produced by the
      compiled reference), two-sample KS at p > 0.01.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -372,7 +374,7 @@ def test_config4_state_populations_vs_reference(golden, dev, inst):
 
 
 # ------------------------------------------------------------------------------------ config 3
-@pytest.mark.parametrize("tau", [10, 30, 100])
+@pytest.mark.parametrize("tau", [10, 30, 100, 300, 1000])
 def test_santoro_residual_energy_vs_tau(golden, dev, tau):
     """BASELINE configs[2] (examples/santoro80.py:23-33): the 80x80 Martonak-Santoro-Tosatti
     instance, P=20, T=0.01, Gamma 1.5 -> 1e-8 in tau steps; residual energy above the known ground
@@ -380,7 +382,9 @@ def test_santoro_residual_energy_vs_tau(golden, dev, tau):
     256 runs of the reference's QuantumAnneal_parallel (golden): KS p > 0.01."""
     import os
     import piqmc.qmc as qmc
-    ref = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_santoro.npz"))["qa_par_%d" % tau]
+    # tau <= 100: 256 reference runs each; tau = 300 / 1000 (the long end of examples/santoro80.py:290-323): 256 / 128
+    fn = "ref_santoro.npz" if tau <= 100 else "ref_santoro_long.npz"
+    ref = np.load(os.path.join(os.path.dirname(__file__), "golden", fn))["qa_par_%d" % tau]
     nbs = golden["vec"]["nbs_santoro_80x80"]
     out = qmc.QuantumAnnealReplicas(np.linspace(1.5, 1e-8, tau), 1, 20, 0.01, 6400, None, nbs, seed=8080 + tau,
                                     order="natural", nreplicas=1024, device=dev)
@@ -588,3 +592,65 @@ def test_path_graph_natural_order_exceeds_one_grid(dev):
     finally:
         dev.set_variant(0)
     assert np.array_equal(want, got)
+
+
+def _integer_instance(n, seed, unit=0.25):
+    """Random graph with couplings and fields in {+-1, +-2, +-3} * unit, at most 6 bonds + 1 field per spin."""
+    rng = np.random.RandomState(seed)
+    rows = [[] for _ in range(n)]
+    for _ in range(3 * n):
+        i, j = rng.randint(n, size=2)
+        if i == j or len(rows[i]) >= 6 or len(rows[j]) >= 6 or any(e[0] == j for e in rows[i]):
+            continue
+        v = unit * rng.choice([-3, -2, -1, 1, 2, 3])
+        rows[i].append((j, v))
+        rows[j].append((i, v))
+    nbs = np.zeros((n, 7, 2))
+    for i in range(n):
+        ent = rows[i] + ([(i, unit * rng.choice([-2, -1, 1, 3]))] if rng.rand() < 0.7 else [])
+        for k, (j, v) in enumerate(ent):
+            nbs[i, k] = (j, v)
+    return nbs
+
+
+@pytest.mark.parametrize("kind,P,T,R", [("qa", 7, 0.3, 70), ("qa", 64, 0.05, 33), ("qa", 20, 2.0, 40),
+                                        ("sa", 64, None, 200), ("sa", 64, None, 4100)])
+def test_resident_integer_kernel_bit_exact(dev, kind, P, T, R):
+    """Couplings that are small integer multiples of a power of two run through the bit-sliced resident kernel
+    (n in five bit planes, thresholds per (sweep, spin) by the warp): equal to the CPU statement, and to the
+    per-lane resident kernel (PIQMC_NO_INT_KERNEL), cold and hot, static colouring and per-sweep orders."""
+    import piqmc.sa as sa
+    n = 24
+    nbs = _integer_instance(n, 11 + P)
+    idx, J32 = O.nbs_to_ell(nbs)
+    color = tools.OrderLevels(nbs)
+    prng = np.random.RandomState(R)
+    for orders in (None, np.stack([prng.permutation(n) for _ in range(12)]).astype(np.int32)):
+        got = []
+        for env in ({"PIQMC_FORCE_INT_KERNEL": "1"}, {}, {"PIQMC_NO_INT_KERNEL": "1"}):   # bit-sliced | hot head per lane, cold tail bit-sliced | per lane
+            os.environ.update(env)
+            try:
+                dev.set_graph(nbs, color)
+                dev.set_variant(5)
+                if kind == "qa":
+                    sched = np.linspace(2.0, 1e-8, 6)
+                    init = O.colour_init_spins(3, 1, R, n)
+                    want = np.repeat(init[:, :, None], P, axis=2).copy()
+                    O.qa_colour(sched, 2, P, T, idx, J32, color, want, 3, replica0=1, sweep0=2, orders=orders)
+                    dev.state_alloc(R, P)
+                    dev.state_init_random(3, 1, tile=True)
+                    dev.qa_colour(sched, 2, T, 3, replica0=1, sweep0=2, orders=orders)
+                    got.append(np.transpose(tools.UnpackWords(dev.state_download_words(), P), (0, 2, 1)))
+                else:
+                    sched = np.linspace(3.0, 0.05, 6)
+                    init = (2 * np.random.RandomState(7).randint(2, size=(R, n)) - 1).astype(np.int8)
+                    want = init.copy()
+                    O.sa_colour(sched, 2, idx, J32, color, want, seed=5, row0=1, orders=orders)
+                    out = sa.AnnealReplicas(sched, 2, init, nbs, 5, color=color if orders is None else None,
+                                            order=orders if orders is not None else "natural", row0=1, device=dev)
+                    got.append(out["spins"])
+            finally:
+                dev.set_variant(0)
+                for k in env:
+                    del os.environ[k]
+            assert np.array_equal(got[-1], want), "env %r" % (env,)

@@ -58,3 +58,40 @@ for inst in ("bipartite8", "hopfield8"):
                 dev.set_variant(0)
             print("%-10s %s  R=%d (%d rows)  %d schedule steps x %d sweeps  variant %d  %.4f s -> %.3e attempts/s"
                   % (inst, kind.upper(), R, rows, sched.size, mcsteps, variant, dt, attempts / dt))
+
+# ---- the +-J instance (bipartite8) in the regime multispin coding is made for: long, cold runs (500 sweeps;
+#      SA T 0.3 -> 0.01, PIQMC T = 0.05 with P = 64 slices), per-lane resident kernel vs bit-sliced resident kernel
+nbs = vec["nbs_bipartite8"]
+color = tools.ColourGraph(nbs, "natural")
+for kind in ("sa", "qa"):
+    for env, label in (({"PIQMC_NO_INT_KERNEL": "1"}, "per-lane"), ({"PIQMC_FORCE_INT_KERNEL": "1"}, "bit-sliced")):
+        os.environ.update(env)
+        try:
+            dev.set_graph(nbs, color)
+            dev.set_variant(5)
+            if kind == "sa":
+                rows, P = (R + 63) // 64, 64
+                dev.state_alloc(rows, 64)
+                ssched = np.linspace(0.3, 0.01, 5)
+                run = lambda: dev.sa_colour(ssched, 100, 11)
+            else:
+                rows, P = R // 8, 64
+                dev.state_alloc(rows, P)
+                qsched = np.linspace(3.0, 1e-8, 5)
+                run = lambda: dev.qa_colour(qsched, 100, 0.05, 11)
+            attempts = float(rows) * P * 8 * 500
+            dev.state_init_random(11, 0, tile=(kind == "qa"))
+            run()
+            dev.synchronize()
+            dev.state_init_random(11, 0, tile=(kind == "qa"))
+            dev.synchronize()
+            t0 = time.perf_counter()
+            run()
+            dev.synchronize()
+            dt = time.perf_counter() - t0
+        finally:
+            dev.set_variant(0)
+            for k in env:
+                del os.environ[k]
+        print("bipartite8 %s cold, 500 sweeps, %d rows x %d lanes, %-10s kernel: %.4f s -> %.3e attempts/s"
+              % (kind.upper(), rows, P, label, dt, attempts / dt))
