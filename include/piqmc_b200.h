@@ -223,6 +223,14 @@ int piqmc_energy(piqmc_handle h, double *energies);
  * download of the words runs on a second stream and overlaps the energy reduction. */
 int piqmc_results(piqmc_handle h, double *energies, uint64_t *words);
 
+/* Histogram of the energies of the last piqmc_energy / piqmc_results on the device (the residual-energy
+ * statistics of examples/santoro80.py:290-323 without moving R x slices doubles to the host): one value per
+ * replica -- reduce 0: mean over its slices, 1: its lowest slice, 2: every slice counts on its own --, binned
+ * as floor(((E - e0) * scale - lo) / (hi - lo) * nbins); counts[nbins] in range, counts[nbins] below lo,
+ * counts[nbins + 1] at or above hi; stats[0..2] = sum, minimum and maximum of (E - e0) * scale. */
+int piqmc_energy_histogram(piqmc_handle h, int reduce, double e0, double scale, double lo, double hi, int nbins,
+                           uint64_t *counts, double *stats);
+
 /* ClassicalIsingEnergy for host configurations: J given as nnz COO triples holding each bond
  * once (diagonal = local fields); spins[c*nspins + i] +-1; energies[c]. */
 int piqmc_energy_coo(piqmc_handle h, int nspins, int nnz, const int32_t *row, const int32_t *col,

@@ -1403,6 +1403,45 @@ int piqmc_energy(piqmc_handle h, double *energies)
     return PIQMC_OK;
 }
 
+int piqmc_energy_histogram(piqmc_handle h, int reduce, double e0, double scale, double lo, double hi, int nbins,
+                           uint64_t *counts, double *stats)
+{
+    USE(h);
+    PIQMC_REQUIRE(h->d_words && h->d_energy, PIQMC_ENOSTATE, "no packed state");
+    PIQMC_REQUIRE(reduce >= 0 && reduce <= 2 && nbins >= 1 && nbins <= (1 << 20) && hi > lo && counts, PIQMC_EINVAL,
+                  "bad histogram arguments");
+    DevBuf<unsigned long long> d_counts;
+    DevBuf<double> d_stats;
+    PIQMC_CUDA(d_counts.alloc(nbins + 2));
+    PIQMC_CUDA(d_stats.alloc(3));
+    // order-preserving integer images of +inf / -inf as the starting minimum / maximum
+    const long long kmax = 0x7FF0000000000000ll, kmin = (long long)(0x8000000000000000ull - 0xFFF0000000000000ull);
+    double init[3] = {0.0, 0.0, 0.0};
+    memcpy(&init[1], &kmax, 8);
+    memcpy(&init[2], &kmin, 8);
+    PIQMC_CUDA(cudaMemsetAsync(d_counts.p, 0, (size_t)(nbins + 2) * sizeof(unsigned long long), h->stream));
+    PIQMC_CUDA(cudaMemcpyAsync(d_stats.p, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+    TRY(launch_energy_histogram(h, reduce, e0, scale, lo, hi, nbins, d_counts.p, d_stats.p));
+    double out[3];
+    PIQMC_CUDA(cudaMemcpyAsync(counts, d_counts.p, (size_t)(nbins + 2) * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+    PIQMC_CUDA(cudaMemcpyAsync(out, d_stats.p, sizeof(out), cudaMemcpyDeviceToHost, h->stream));
+    PIQMC_CUDA(cudaStreamSynchronize(h->stream));
+    if (stats) {
+        auto unkey = [](double x) {
+            long long k;
+            memcpy(&k, &x, 8);
+            if (k < 0) k = (long long)(0x8000000000000000ull - (unsigned long long)k);
+            double v;
+            memcpy(&v, &k, 8);
+            return v;
+        };
+        stats[0] = out[0];
+        stats[1] = unkey(out[1]);
+        stats[2] = unkey(out[2]);
+    }
+    return PIQMC_OK;
+}
+
 int piqmc_results(piqmc_handle h, double *energies, uint64_t *words)
 {
     USE(h);

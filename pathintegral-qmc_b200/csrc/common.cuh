@@ -242,6 +242,8 @@ int launch_resident_sweeps(piqmc_ctx *c, int qa, int trotter, const int32_t *d_o
 bool resident_int_ok(const piqmc_ctx *c, int qa, int trotter);
 int resident_rows_per_block(const piqmc_ctx *c, int qa);
 int launch_energy(piqmc_ctx *c);
+int launch_energy_histogram(piqmc_ctx *c, int reduce, double e0, double scale, double lo, double hi, int nbins,
+                            unsigned long long *d_counts, double *d_stats);
 int launch_energy_coo(piqmc_ctx *c, int nspins, int nnz, const int32_t *d_row, const int32_t *d_col,
                       const double *d_val, int nconfs, const int8_t *d_spins, double *d_out);
 // the production kernel: nsweeps sweeps in one dataflow launch (colour_fast.cu)

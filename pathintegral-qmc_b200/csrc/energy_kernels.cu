@@ -83,7 +83,68 @@ __global__ void __launch_bounds__(256) energy_coo_kernel(
     if (threadIdx.x == 0) out[blockIdx.x] = -sh[0];
 }
 
+// one thread per replica (or per (replica, slice) when reduce == 2): value -> bin; block-level sums first
+__global__ void __launch_bounds__(256) energy_histogram_kernel(
+    const double *__restrict__ en, int nreplicas, int slices, int reduce, double e0, double scale, double lo,
+    double hi, int nbins, unsigned long long *__restrict__ counts, double *__restrict__ stats)
+{
+    const int n = reduce == 2 ? nreplicas * slices : nreplicas;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    double v = 0.0;
+    const bool on = tid < n;
+    if (on) {
+        if (reduce == 2) v = en[tid];
+        else {
+            const double *e = en + (size_t)tid * slices;
+            double acc = e[0];
+            for (int k = 1; k < slices; k++) acc = reduce == 0 ? acc + e[k] : fmin(acc, e[k]);
+            v = reduce == 0 ? acc / slices : acc;
+        }
+        v = (v - e0) * scale;
+        int b;
+        if (v < lo) b = nbins;
+        else if (!(v < hi)) b = nbins + 1;
+        else b = min(nbins - 1, (int)((v - lo) / (hi - lo) * nbins));
+        atomicAdd(counts + b, 1ull);
+    }
+    __shared__ double ssum[256], smin[256], smax[256];
+    ssum[threadIdx.x] = on ? v : 0.0;
+    smin[threadIdx.x] = on ? v : 1e300;
+    smax[threadIdx.x] = on ? v : -1e300;
+    __syncthreads();
+    for (int st = 128; st > 0; st >>= 1) {
+        if (threadIdx.x < st) {
+            ssum[threadIdx.x] += ssum[threadIdx.x + st];
+            smin[threadIdx.x] = fmin(smin[threadIdx.x], smin[threadIdx.x + st]);
+            smax[threadIdx.x] = fmax(smax[threadIdx.x], smax[threadIdx.x + st]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        atomicAdd(stats, ssum[0]);
+        // minimum / maximum through the order-preserving integer image of a double
+        auto key = [](double x) {
+            long long k = __double_as_longlong(x);
+            return k >= 0 ? k : (long long)(0x8000000000000000ull - (unsigned long long)k);
+        };
+        atomicMin(reinterpret_cast<long long *>(stats) + 1, key(smin[0]));
+        atomicMax(reinterpret_cast<long long *>(stats) + 2, key(smax[0]));
+    }
+}
+
 }  // namespace
+
+int launch_energy_histogram(piqmc_ctx *c, int reduce, double e0, double scale, double lo, double hi, int nbins,
+                            unsigned long long *d_counts, double *d_stats)
+{
+    const int slices = c->seg_P, nrep = c->nrows * c->seg_S;
+    const int n = reduce == 2 ? nrep * slices : nrep;
+    energy_histogram_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_energy, nrep, slices, reduce, e0, scale, lo, hi,
+                                                                   nbins, d_counts, d_stats);
+    c->launches++;
+    PIQMC_CUDA(cudaGetLastError());
+    return PIQMC_OK;
+}
 
 int launch_energy(piqmc_ctx *c)
 {

@@ -365,6 +365,21 @@ class Device:
         return (en.reshape(self.nrows * self.per_word, self.lanes // self.per_word),
                 self._unpack_replicas(words_out))
 
+    def energy_histogram(self, e0=0.0, scale=1.0, lo=0.0, hi=1.0, nbins=64, reduce="mean"):
+        """Histogram of (E - e0) * scale over the replicas of the last energy() / results() call, on the device
+        (e.g. e0 = ground-state energy, scale = 1 / nspins: residual energy per spin, examples/santoro80.py:290-323
+        of the reference).  reduce: "mean" over a replica's slices, "min" (its best slice) or "all" (every slice).
+        Returns dict(counts uint64[nbins], below, above, mean, min, max, edges float64[nbins + 1])."""
+        mode = {"mean": 0, "min": 1, "all": 2}[reduce]
+        counts = np.zeros(int(nbins) + 2, dtype=np.uint64)
+        stats = np.zeros(3, dtype=np.float64)
+        check(lib.piqmc_energy_histogram(self._h, mode, float(e0), float(scale), float(lo), float(hi), int(nbins),
+                                         _ptr(counts), _ptr(stats)))
+        total = int(counts.sum())
+        return {"counts": counts[:nbins], "below": int(counts[nbins]), "above": int(counts[nbins + 1]),
+                "mean": stats[0] / max(total, 1), "min": stats[1], "max": stats[2],
+                "edges": np.linspace(lo, hi, int(nbins) + 1)}
+
     def energy_coo(self, nspins, row, col, val, spins):
         row = np.ascontiguousarray(row, dtype=np.int32)
         col = np.ascontiguousarray(col, dtype=np.int32)

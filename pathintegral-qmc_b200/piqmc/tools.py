@@ -9,7 +9,7 @@ import scipy.sparse as sps
 
 __all__ = ["bits2spins", "spins2bits", "GenerateNeighbors", "Generate2DIsingInstance",
            "ColourGraph", "OrderLevels", "LoadIsingInstance", "IsingFromTriples", "GaussianTorusNeighbors", "TorusNaturalLevels",
-           "PackWords", "UnpackWords"]
+           "PackWords", "UnpackWords", "NeighborsToCSR", "CSRToNeighbors"]
 
 
 def bits2spins(vec):
@@ -24,7 +24,7 @@ def spins2bits(vec):
     return [0 if k == 1 else 1 for k in vec]
 
 
-def GenerateNeighbors(nspins, J, maxnb, savepath=None, colouring=None):
+def GenerateNeighbors(nspins, J, maxnb, savepath=None, colouring=None, format="ell"):
     """Neighbour table of the Ising graph @J: float64[nspins, maxnb, 2] with
     [:, :, 0] = neighbour index and [:, :, 1] = coupling; a diagonal entry J[i,i] (local field)
     appears as a self-neighbour of i; unused rows stay [0, 0].
@@ -37,9 +37,13 @@ def GenerateNeighbors(nspins, J, maxnb, savepath=None, colouring=None):
 
     @colouring (not in the reference): None returns the table alone, like the reference;
     "natural" / "checkerboard" / an int order array returns (table, colour classes) with the
-    classes of ColourGraph(table, colouring) -- what the production kernels sweep by."""
+    classes of ColourGraph(table, colouring) -- what the production kernels sweep by.
+    @format (not in the reference): "ell" the table; "csr" the (indptr, indices, data) triple of
+    NeighborsToCSR(table)."""
     nspins = int(nspins)
     maxnb = int(maxnb)
+    if format not in ("ell", "csr"):
+        raise ValueError("format must be 'ell' or 'csr'")
     nbs = np.zeros((nspins, maxnb, 2))
     fill = np.zeros(nspins, dtype=np.int64)
     Jd = J.todok()
@@ -58,8 +62,37 @@ def GenerateNeighbors(nspins, J, maxnb, savepath=None, colouring=None):
             fill[ispin] = k + 1
     if savepath is not None:
         np.save(savepath, nbs)
+    out = nbs if format == "ell" else NeighborsToCSR(nbs)
     if colouring is not None:
-        return nbs, ColourGraph(nbs, colouring)
+        return out, ColourGraph(nbs, colouring)
+    return out
+
+
+def NeighborsToCSR(nbs):
+    """CSR form of a neighbour table (the north-star's "ELL/CSR"): (indptr int64[N+1], indices int32[nnz],
+    data float64[nnz]); row i holds the entries of table row i with a non-zero coupling, in table order, a
+    local field as the self entry (i, J_ii) -- every bond therefore appears in the rows of both its spins, as
+    in the table of tools.pyx:74-96."""
+    nbs = np.asarray(nbs, dtype=np.float64)
+    live = nbs[:, :, 1] != 0.0
+    indptr = np.concatenate([[0], np.cumsum(live.sum(axis=1))]).astype(np.int64)
+    return indptr, nbs[:, :, 0][live].astype(np.int32), nbs[:, :, 1][live].copy()
+
+
+def CSRToNeighbors(indptr, indices, data, maxnb=None):
+    """The neighbour table float64[N, maxnb, 2] of a CSR graph in the convention of NeighborsToCSR (maxnb:
+    the longest row unless given; a longer row raises IndexError like GenerateNeighbors)."""
+    indptr = np.asarray(indptr, dtype=np.int64)
+    n = indptr.size - 1
+    deg = np.diff(indptr)
+    width = int(deg.max()) if maxnb is None else int(maxnb)
+    if n and deg.max() > width:
+        raise IndexError("Out of bounds on buffer access (axis 1)")
+    nbs = np.zeros((n, max(width, 1), 2))
+    col = np.arange(indptr[-1]) - np.repeat(indptr[:-1], deg)
+    row = np.repeat(np.arange(n), deg)
+    nbs[row, col, 0] = np.asarray(indices)
+    nbs[row, col, 1] = np.asarray(data, dtype=np.float64)
     return nbs
 
 

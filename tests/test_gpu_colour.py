@@ -654,3 +654,21 @@ def test_resident_integer_kernel_bit_exact(dev, kind, P, T, R):
                 for k in env:
                     del os.environ[k]
             assert np.array_equal(got[-1], want), "env %r" % (env,)
+
+
+def test_energy_histogram_on_device(golden, dev):
+    """piqmc_energy_histogram == numpy on the downloaded energies, for the three reductions."""
+    import piqmc.qmc as qmc
+    nbs = golden["vec"]["nbs_inst_0_32x32"]
+    out = qmc.QuantumAnnealReplicas(np.linspace(1.5, 1e-8, 20), 1, 20, 0.01, 1024, None, nbs, 5, order="natural",
+                                    nreplicas=301, device=dev)
+    en = out["energies"]
+    gs, n = -1591.9166416866, 1024
+    for reduce, val in (("mean", en.mean(axis=1)), ("min", en.min(axis=1)), ("all", en.reshape(-1))):
+        v = (val - gs) / n
+        lo, hi = 0.2, 0.3
+        h = dev.energy_histogram(e0=gs, scale=1.0 / n, lo=lo, hi=hi, nbins=25, reduce=reduce)
+        ref = np.histogram(v[(v >= lo) & (v < hi)], bins=25, range=(lo, hi))[0]
+        assert np.array_equal(h["counts"], ref.astype(np.uint64))
+        assert h["below"] == int((v < lo).sum()) and h["above"] == int((v >= hi).sum())
+        np.testing.assert_allclose([h["mean"], h["min"], h["max"]], [v.mean(), v.min(), v.max()], rtol=1e-12)

@@ -195,3 +195,24 @@ def test_level_colouring_equals_sequential_sweep_on_random_graphs(seed):
     O.sa_colour(np.linspace(2.0, 0.3, nsweeps), 1, idx, J32, levels, a, 9)
     O.sa_colour(np.linspace(2.0, 0.3, nsweeps), 1, idx, J32, levels, b, 9, orders=np.tile(order, (nsweeps, 1)))
     assert np.array_equal(a, b)
+
+
+def test_csr_form_of_the_neighbour_table(golden):
+    """GenerateNeighbors(format="csr") / NeighborsToCSR / CSRToNeighbors: rows in table order, local fields as
+    self entries, every bond in both rows; the round trip gives the table back (pads are zeros)."""
+    for inst in ("boixo", "bipartite8", "hopfield8", "inst_0_32x32"):
+        nbs = golden["vec"]["nbs_" + inst]
+        indptr, indices, data = tools.NeighborsToCSR(nbs)
+        n = nbs.shape[0]
+        assert indptr.shape == (n + 1,) and indptr[-1] == indices.size == data.size == np.count_nonzero(nbs[:, :, 1])
+        for i in (0, n // 2, n - 1):
+            row = nbs[i][nbs[i, :, 1] != 0.0]
+            assert np.array_equal(indices[indptr[i]:indptr[i + 1]], row[:, 0].astype(np.int32))
+            assert np.array_equal(data[indptr[i]:indptr[i + 1]], row[:, 1])
+        back = tools.CSRToNeighbors(indptr, indices, data, maxnb=nbs.shape[1])
+        live = nbs[:, :, 1] != 0.0
+        # the table may keep zero-valued entries between live ones; compare the live entries row by row
+        for i in range(n):
+            assert np.array_equal(back[i][back[i, :, 1] != 0.0], nbs[i][live[i]])
+    with pytest.raises(IndexError):
+        tools.CSRToNeighbors(indptr, indices, data, maxnb=1)
