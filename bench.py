@@ -229,7 +229,8 @@ def run_ours(args):
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
-    from piqmc.shard import gather_energies, shard_replicas
+    from piqmc.shard import bind_to_gpu_numa, gather_energies, shard_replicas
+    numa_cores = bind_to_gpu_numa(local) if (world > 1 and not os.environ.get("PIQMC_NO_NUMA_BIND")) else 0
     replica0, R = shard_replicas(R_TOTAL, world, rank)
     n = L * L
     K, W = args.steps, args.warmup
@@ -347,7 +348,7 @@ def run_ours(args):
         "roofline_smem": {"achieved": B_ALG_SMEM * value / world / 1e9, "peak": smem_peak, "unit": "GB/s",
                           "frac": B_ALG_SMEM * value / world / 1e9 / smem_peak,
                           "bytes_per_attempt": B_ALG_SMEM, "peak_source": "128 B/clk/SM x %d SMs x %.0f MHz" % (nsm, sm_mhz)},
-        "gather_ms": gather_ms,
+        "gather_ms": gather_ms, "host_cores_bound_per_rank": numa_cores,
         "energy_per_spin": {"mean_over_slices": float(en.mean() / n), "best_slice_mean": float(en.min(axis=1).mean() / n)},
     }
     # ---- the deterministic (bit-exact replay) path: one drop-in call and a batch, reported next to the headline

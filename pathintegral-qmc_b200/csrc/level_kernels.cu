@@ -1206,11 +1206,19 @@ int launch_level_sweeps(piqmc_ctx *c, int qa, int nsweeps, int mcsteps, int f_of
     a.stream_len = 0;
     if (streamed) {
         warps = LV_MAXW;
-        if (int rc = level_build_stream(c, K * warps)) return rc;
+        if (int rc = level_build_stream(c, K * warps)) {
+            cudaStreamSynchronize(c->stream);
+            cudaFree(d_par);
+            return rc;
+        }
         a.stream = c->d_stream;
         a.stream_len = c->stream_len;
-        PIQMC_REQUIRE((long long)c->stream_len * ((long long)nsweeps + nperiods_extra) < (1ll << 31), PIQMC_EINVAL,
-                      "too many sweeps for one call of the streamed level kernel");
+        if ((long long)c->stream_len * ((long long)nsweeps + nperiods_extra) >= (1ll << 31)) {
+            cudaStreamSynchronize(c->stream);
+            cudaFree(d_par);
+            piqmc_set_error("too many sweeps for one call of the streamed level kernel");
+            return PIQMC_EINVAL;
+        }
     }
     a.nperiods_extra = nperiods_extra;
     a.xrecs = c->d_xrecs;

@@ -320,8 +320,9 @@ class Device:
         return o
 
     def qa_colour(self, sched, mcsteps, temp, seed, replica0=0, sweep0=0, trotter=0, orders=None):
-        """QA sweeps over the resident state.  orders=None: the graph's colouring, asynchronous
-        (returns once the launches are queued).  orders int32[nsweeps, N]: sweep s is the
+        """QA sweeps over the resident state (returns when they have run: the library synchronises its stream,
+        the per-sweep parameter arrays live only for the call).  orders=None: the graph's colouring.
+        orders int32[nsweeps, N]: sweep s is the
         sequential sweep visiting spins in orders[s] (run through its level colouring)."""
         sched = np.ascontiguousarray(sched, dtype=np.float64)
         o = self._orders(orders, sched.size * int(mcsteps))

@@ -21,6 +21,27 @@ def shard_replicas(nreplicas, world_size, rank):
     return replica0, count
 
 
+def bind_to_gpu_numa(gpu_index):
+    """Pin this process to the CPU cores next to GPU `gpu_index` (NVML's ideal affinity) before it allocates
+    its pinned host buffers: with one process per GPU the eight result downloads of a box then land in the
+    memory of the socket their GPU hangs on instead of all crossing to one node.  Returns the number of cores
+    bound to, or 0 when NVML or the affinity call is not available (nothing changes then)."""
+    try:
+        import os
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(gpu_index))
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * w + b for w in range(words) for b in range(64) if (int(mask[w]) >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 def gather_rows(local, nreplicas, group=None):
     """All-gather a per-replica tensor (first dimension = this rank's replicas, sharded with
     shard_replicas) into the full [nreplicas, ...] tensor, in global replica order, on every
