@@ -183,6 +183,15 @@ void *piqmc_energy_devptr(piqmc_handle h);
 int piqmc_qa_colour(piqmc_handle h, const double *sched, int nsched, int mcsteps, float temp,
                     uint64_t seed, uint32_t replica0, uint32_t sweep0, int trotter,
                     const int32_t *orders);
+/* The AS-SHIPPED semantics of qmc.QuantumAnneal (piqmc/qmc.pyx:98-136) on the resident state: the running
+ * energy difference is reset once per slice sweep, not per spin, so within a slice it is a float32 carry over
+ * all spins visited so far (the reference's default function behaves like this; its `_parallel` variant and
+ * piqmc_qa_colour reset per spin).  Trotter neighbours slices-1 and 1 for every slice, `> 0` shortcut,
+ * orders int32[nsched*mcsteps][nspins] = the visiting order of every sweep, shared by all replicas (NULL:
+ * 0..N-1), this library's Philox uniforms.  One warp per replica; any maxnb; one replica per word.
+ * Specification: oracle_qa_carry (oracle/piqmc_oracle.c part 4). */
+int piqmc_qa_carry(piqmc_handle h, const double *sched, int nsched, int mcsteps, float temp,
+                   uint64_t seed, uint32_t replica0, uint32_t sweep0, const int32_t *orders);
 /* Classical SA sweeps over the resident state (lanes = 64 replicas per word, sa.Anneal rules). */
 int piqmc_sa_colour(piqmc_handle h, const double *sched, int nsched, int mcsteps,
                     uint64_t seed, uint32_t row0, uint32_t sweep0, const int32_t *orders);

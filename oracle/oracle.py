@@ -81,6 +81,10 @@ def lib():
         L.oracle_colour_initbit.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32]
         L.oracle_colour_thresh.restype = ctypes.c_uint32
         L.oracle_colour_thresh.argtypes = [ctypes.c_float]
+        L.oracle_qa_carry.restype = None
+        L.oracle_qa_carry.argtypes = [c_dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int,
+                                      ctypes.c_int, c_ip, c_fp, ctypes.c_int, c_bp, ctypes.c_uint64, ctypes.c_uint32,
+                                      ctypes.c_uint32, c_ip]
         L.oracle_qa_colour.restype = None
         L.oracle_qa_colour.argtypes = [c_dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                        ctypes.c_int, ctypes.c_int, c_ip, c_fp, ctypes.c_int, c_ip,
@@ -283,6 +287,20 @@ def qa_colour(sched, mcsteps, slices, temp, idx, J, color, spins, seed, replica0
                            N, idx.shape[1], _p(idx, c_ip), _p(J, c_fp), int(color.max()) + 1,
                            _p(color, c_ip), R, _p(spins, c_bp), seed, replica0, sweep0, trotter,
                            _orders(orders, sched.size * mcsteps, N)[1])
+
+
+def qa_carry(sched, mcsteps, slices, temp, idx, J, spins, seed, replica0=0, sweep0=0, orders=None):
+    """The as-shipped QuantumAnneal semantics (per-slice energy carry) with Philox uniforms; spins int8[R,N,P]
+    in place; orders int32[nsweeps,N] or None (0..N-1)."""
+    sched = np.ascontiguousarray(sched, dtype=np.float64)
+    idx = np.ascontiguousarray(idx, dtype=np.int32)
+    J = np.ascontiguousarray(J, dtype=np.float32)
+    assert spins.dtype == np.int8 and spins.flags.c_contiguous and spins.ndim == 3
+    R, N, P = spins.shape
+    assert P == slices and idx.shape == J.shape == (N, idx.shape[1])
+    lib().oracle_qa_carry(_p(sched, c_dp), sched.size, mcsteps, slices, ctypes.c_float(temp), N, idx.shape[1],
+                          _p(idx, c_ip), _p(J, c_fp), R, _p(spins, c_bp), seed, replica0, sweep0,
+                          _orders(orders, sched.size * mcsteps, N)[1])
 
 
 def sa_colour(sched, mcsteps, idx, J, color, spins, seed, row0=0, sweep0=0, orders=None):

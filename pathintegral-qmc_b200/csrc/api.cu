@@ -1377,6 +1377,43 @@ int piqmc_qa_colour(piqmc_handle h, const double *sched, int nsched, int mcsteps
     return run_colour_sweeps(h, 1, trotter, nsched, mcsteps, jp2, invT, seed, replica0, sweep0, orders);
 }
 
+int piqmc_qa_carry(piqmc_handle h, const double *sched, int nsched, int mcsteps, float temp, uint64_t seed,
+                   uint32_t replica0, uint32_t sweep0, const int32_t *orders)
+{
+    USE(h);
+    PIQMC_REQUIRE(h->d_words, PIQMC_ENOSTATE, "no packed state (call piqmc_state_alloc)");
+    PIQMC_REQUIRE(sched && nsched >= 0 && mcsteps >= 0, PIQMC_EINVAL, "bad schedule");
+    PIQMC_REQUIRE(h->seg_S == 1, PIQMC_EINVAL, "the carry sweeps work on states with one replica per word");
+    const int slices = h->seg_P, N = h->nspins;
+    PIQMC_REQUIRE(slices >= 2, PIQMC_EINVAL, "slices must be >= 2");
+    PIQMC_REQUIRE((float)slices * temp != 0.0f && temp != 0.0f, PIQMC_EZERODIV, "float division");
+    const size_t nsweeps = (size_t)nsched * mcsteps;
+    if (nsweeps == 0) return PIQMC_OK;
+    if (orders) TRY(check_orders(N, nsweeps, orders));
+    std::vector<float> a(nsweeps), b(nsweeps, 1.0f / temp);
+    for (size_t s = 0; s < nsweeps; s++) a[s] = 2.0f * piqmc_jperp(sched[s / mcsteps], slices, temp);
+    DevBuf<float> d_jp2, d_invT;
+    PIQMC_CUDA(d_jp2.alloc(nsweeps));
+    PIQMC_CUDA(d_invT.alloc(nsweeps));
+    PIQMC_CUDA(cudaMemcpyAsync(d_jp2.p, a.data(), nsweeps * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    PIQMC_CUDA(cudaMemcpyAsync(d_invT.p, b.data(), nsweeps * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    if (!orders) {
+        TRY(launch_qa_carry(h, nullptr, 0, (int)nsweeps, d_jp2.p, d_invT.p, seed, replica0, sweep0));
+        PIQMC_CUDA(cudaStreamSynchronize(h->stream));
+        return PIQMC_OK;
+    }
+    const size_t chunk = std::max<size_t>(1, std::min<size_t>(nsweeps, (size_t)(64u << 20) / ((size_t)N * 4)));
+    DevBuf<int32_t> d_ord;
+    PIQMC_CUDA(d_ord.alloc(chunk * N));
+    for (size_t base = 0; base < nsweeps; base += chunk) {
+        const size_t m = std::min(chunk, nsweeps - base);
+        PIQMC_CUDA(cudaMemcpyAsync(d_ord.p, orders + base * N, m * N * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+        TRY(launch_qa_carry(h, d_ord.p, 1, (int)m, d_jp2.p + base, d_invT.p + base, seed, replica0, sweep0 + (uint32_t)base));
+        PIQMC_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    return PIQMC_OK;
+}
+
 int piqmc_sa_colour(piqmc_handle h, const double *sched, int nsched, int mcsteps, uint64_t seed,
                     uint32_t row0, uint32_t sweep0, const int32_t *orders)
 {

@@ -393,6 +393,75 @@ __global__ void __launch_bounds__(128) resident_sweeps_int(
 }
 
 // ------------------------------------------------------------------------------------------
+// Carry mode: the AS-SHIPPED semantics of qmc.QuantumAnneal (piqmc/qmc.pyx:98-136) at production speed.
+// The reference resets its running energy difference once per slice, not per spin: within a slice sweep
+// ediff is a float32 carry over all spins visited so far, and the carry decides the moves.  A slice is
+// therefore one sequential chain per sweep -- but the slices of a replica only meet in the Trotter terms,
+// which read slices P-1 and 1 of the spin being visited, and every spin is visited once per sweep: the P
+// chains of a replica can advance in lockstep over the visiting order if, at every step, slice 1 decides
+// first (slice 0 still sees its old value, slices >= 2 its new one) and everybody reads slice P-1 before it
+// moves.  One warp = one replica (row); lane l carries the chains of slices l and l + 32; the word of the
+// visited spin and its neighbours are warp-uniform loads; the flips of a step are collected by ballot.
+// Specification: oracle_qa_carry (oracle/piqmc_oracle.c part 4), bit for bit.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) qa_carry_kernel(
+    uint64_t *__restrict__ words, int nspins, int nrows, int maxnb, const int32_t *__restrict__ idx,
+    const float *__restrict__ J32, const int32_t *__restrict__ order, int per_sweep_orders, int nsweeps,
+    const float *__restrict__ jp2s, const float *__restrict__ invTs, int lanes, uint32_t k0, uint32_t k1,
+    uint32_t row0, uint32_t sweep0)
+{
+    const int lane = threadIdx.x & 31;
+    const int row = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (row >= nrows) return;                                  // whole warps
+    uint64_t *wrow = words + row;
+    const uint32_t prow = row0 + (uint32_t)row;
+    const int top = lanes - 1;
+    for (int s = 0; s < nsweeps; s++) {
+        const float invT = invTs[s];
+        const float njp2 = -jp2s[s];
+        const uint32_t sweep = sweep0 + (uint32_t)s;
+        const int32_t *ord = per_sweep_orders ? order + (size_t)s * nspins : order;
+        float ed[2] = {0.0f, 0.0f};                            // the carries of slices lane, lane + 32
+        for (int t = 0; t < nspins; t++) {
+            const int i = ord ? __ldg(ord + t) : t;
+            const uint64_t w = __ldcg(wrow + (size_t)i * nrows);
+            // in-slice terms, table order
+#pragma unroll 1
+            for (int n = 0; n < maxnb; n++) {
+                const int j = __ldg(idx + (size_t)i * maxnb + n);
+                const float negJ2 = -2.0f * __ldg(J32 + (size_t)i * maxnb + n);
+                const uint64_t x = (j == i) ? w : (w ^ __ldcg(wrow + (size_t)j * nrows));
+                ed[0] = __fadd_rn(ed[0], flip_sign(negJ2, (uint32_t)(x >> lane) & 1u));
+                ed[1] = __fadd_rn(ed[1], flip_sign(negJ2, (uint32_t)(x >> (lane + 32)) & 1u));
+            }
+            const uint32_t old_top = (uint32_t)(w >> top) & 1u, old1 = (uint32_t)(w >> 1) & 1u;
+            // the decision of slice k with the right-hand Trotter neighbour's bit `rb`: carries on, no reset
+            auto decide = [&](int k, int h, uint32_t rb) -> bool {
+                const uint32_t own = (uint32_t)(w >> k) & 1u;
+                float e = __fadd_rn(ed[h], flip_sign(njp2, own ^ (k == top ? own : old_top)));
+                e = __fadd_rn(e, flip_sign(njp2, own ^ rb));
+                ed[h] = e;
+                if (e > 0.0f) return true;
+                const float x = __fmul_rn(e, invT);
+                if (!(x >= PIQMC_XCUT)) return false;
+                const u32x4 r = philox4x32_10((uint32_t)i, (uint32_t)(k >> 2) | (PIQMC_STREAM_CARRY << 16), sweep, prow, k0, k1);
+                const uint32_t u = (k & 3) == 0 ? r.x : ((k & 3) == 1 ? r.y : ((k & 3) == 2 ? r.z : r.w));
+                return u < colour_thresh(x);
+            };
+            // slice 1 first (its right-hand neighbour is itself)
+            bool f0 = false, f1 = false;
+            if (lane == 1) f0 = decide(1, 0, old1);
+            const uint32_t new1 = old1 ^ (uint32_t)__shfl_sync(0xffffffffu, (int)f0, 1);
+            if (lane != 1 && lane < lanes) f0 = decide(lane, 0, lane == 0 ? old1 : new1);
+            if (lane + 32 < lanes) f1 = decide(lane + 32, 1, new1);
+            const uint32_t lo = __ballot_sync(0xffffffffu, f0), hi = __ballot_sync(0xffffffffu, f1);
+            if (lane == 0) wrow[(size_t)i * nrows] = w ^ (((uint64_t)hi << 32) | lo);
+            __syncwarp();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // state initialisation / packing
 // ------------------------------------------------------------------------------------------
 // all lanes of a segment of P lanes
@@ -591,6 +660,20 @@ int launch_resident_sweeps(piqmc_ctx *c, int qa, int trotter, const int32_t *d_o
     if (c->lanes <= 32) return launch_resident_t<32, true, 0, 1>(RS_ARGS);
     return launch_resident_t<64, true, 0, 1>(RS_ARGS);
 #undef RS_ARGS
+}
+
+// as-shipped QuantumAnneal semantics (per-slice energy carry): d_order null = natural order
+int launch_qa_carry(piqmc_ctx *c, const int32_t *d_order, int per_sweep_orders, int nsweeps, const float *d_jp2,
+                    const float *d_invT, uint64_t seed, uint32_t row0, uint32_t sweep0)
+{
+    if (nsweeps <= 0) return PIQMC_OK;
+    const int wpb = 8;
+    qa_carry_kernel<<<(unsigned)((c->nrows + wpb - 1) / wpb), wpb * 32, 0, c->stream>>>(
+        c->d_words, c->nspins, c->nrows, c->maxnb, c->d_idx, c->d_J32, d_order, per_sweep_orders, nsweeps, d_jp2, d_invT,
+        c->lanes, (uint32_t)seed, (uint32_t)(seed >> 32), row0, sweep0);
+    c->launches++;
+    PIQMC_CUDA(cudaGetLastError());
+    return PIQMC_OK;
 }
 
 int launch_colour_sweep(piqmc_ctx *c, int qa, int trotter, const int32_t *members, int nmem, float jp2,

@@ -171,6 +171,7 @@ struct piqmc_ctx {
 #define PIQMC_STREAM_SWEEP 0u
 #define PIQMC_STREAM_INIT 1u
 #define PIQMC_STREAM_GLOBAL 2u
+#define PIQMC_STREAM_CARRY 4u   // the carry (as-shipped) QA sweeps
 #define PIQMC_STREAM_SA 3u      // SA sweeps: a pre-anneal and the anneal that follows may share a seed
 #define PIQMC_XCUT (-22.0f)
 
@@ -241,6 +242,8 @@ int launch_resident_sweeps(piqmc_ctx *c, int qa, int trotter, const int32_t *d_o
                            int bit_sliced);
 bool resident_int_ok(const piqmc_ctx *c, int qa, int trotter);
 int resident_rows_per_block(const piqmc_ctx *c, int qa);
+int launch_qa_carry(piqmc_ctx *c, const int32_t *d_order, int per_sweep_orders, int nsweeps, const float *d_jp2,
+                    const float *d_invT, uint64_t seed, uint32_t row0, uint32_t sweep0);
 int launch_energy(piqmc_ctx *c);
 int launch_energy_histogram(piqmc_ctx *c, int reduce, double e0, double scale, double lo, double hi, int nbins,
                             unsigned long long *d_counts, double *d_stats);

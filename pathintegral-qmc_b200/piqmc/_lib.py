@@ -68,6 +68,7 @@ SIGNATURES = {
     "piqmc_state_devptr": (c_void, [c_void]),
     "piqmc_energy_devptr": (c_void, [c_void]),
     "piqmc_qa_colour": (c_int, [c_void, c_void, c_int, c_int, c_f, c_u64, c_u32, c_u32, c_int, c_void]),
+    "piqmc_qa_carry": (c_int, [c_void, c_void, c_int, c_int, c_f, c_u64, c_u32, c_u32, c_void]),
     "piqmc_sa_colour": (c_int, [c_void, c_void, c_int, c_int, c_u64, c_u32, c_u32, c_void]),
     "piqmc_set_variant": (c_int, [c_void, c_int]),
     "piqmc_set_chain": (c_int, [c_void, c_int]),

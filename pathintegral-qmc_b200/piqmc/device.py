@@ -329,6 +329,15 @@ class Device:
         check(lib.piqmc_qa_colour(self._h, _ptr(sched), sched.size, int(mcsteps), ctypes.c_float(temp),
                                   int(seed), int(replica0), int(sweep0), int(trotter), _ptr(o)))
 
+    def qa_carry(self, sched, mcsteps, temp, seed, replica0=0, sweep0=0, orders=None):
+        """QA sweeps with the AS-SHIPPED semantics of qmc.QuantumAnneal (energy difference carried over a whole
+        slice sweep, piqmc/qmc.pyx:98-136) over the resident state; orders int32[nsweeps, N] = the visiting order
+        of every sweep, shared by all replicas (None: 0..N-1)."""
+        sched = np.ascontiguousarray(sched, dtype=np.float64)
+        o = self._orders(orders, sched.size * int(mcsteps))
+        check(lib.piqmc_qa_carry(self._h, _ptr(sched), sched.size, int(mcsteps), ctypes.c_float(temp), int(seed),
+                                 int(replica0), int(sweep0), _ptr(o)))
+
     def sa_colour(self, sched, mcsteps, seed, row0=0, sweep0=0, orders=None):
         sched = np.ascontiguousarray(sched, dtype=np.float64)
         o = self._orders(orders, sched.size * int(mcsteps))

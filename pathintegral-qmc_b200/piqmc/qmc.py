@@ -126,7 +126,7 @@ def QuantumAnneal_parallel(sched, mcsteps, slices, temp, nspins, confs, nbs, nth
 def QuantumAnnealReplicas(sched, mcsteps, slices, temp, nspins, spins0, nbs, seed, order="natural",
                           color=None, replica0=0, trotter="reference", device=None, energies=True,
                           tile=True, nreplicas=None, download=True, words_out=None, global_moves=False,
-                          per_word="auto"):
+                          per_word="auto", semantics="parallel"):
     """Production PIQMC: R replicas x `slices` Trotter slices x nspins, one uint64 word per
     (replica, spin) holding all slices, colour-class Metropolis sweeps with Philox4x32-10 keyed by
     (seed; spin, slice, sweep, replica0 + r), J_perp recomputed per schedule step.
@@ -140,6 +140,12 @@ def QuantumAnnealReplicas(sched, mcsteps, slices, temp, nspins, spins0, nbs, see
                        from the natural-order sweep, see DESIGN.md);
         int32[N] / int32[nsweeps,N]  explicit visiting order(s).
     color: explicit colour classes (overrides order).
+    semantics: "parallel" (default) resets the energy difference per spin, like qmc.QuantumAnneal_parallel;
+        "reference" is the AS-SHIPPED qmc.QuantumAnneal (qmc.pyx:98-136): the energy difference is reset once
+        per slice sweep and carried over all spins in between -- markedly different statistics (residual energy
+        1.00 per spin on inst_0_32x32 against 0.25).  It runs sequentially in the visiting order (order=
+        "permutation" is the reference's; "natural" or explicit orders also work), one warp per replica, and
+        takes one replica per word, the reference Trotter neighbours and no world-line moves.
     global_moves: also attempt a world-line move (flip the spin in all slices at once) after the
         local moves of every spin -- not in the reference; off by default.
 
@@ -160,10 +166,20 @@ def QuantumAnnealReplicas(sched, mcsteps, slices, temp, nspins, spins0, nbs, see
     if not 2 <= slices <= 64:
         raise ValueError("the packed colour path supports 2 <= slices <= 64 (got %d)" % slices)
     d = device or _dev.default_device()
+    if semantics not in ("parallel", "reference"):
+        raise ValueError("semantics must be 'parallel' or 'reference'")
+    carry = semantics == "reference"
+    if carry and (global_moves or TROTTER[trotter] != 0 or color is not None or per_word not in ("auto", 1)):
+        raise ValueError("semantics='reference' takes a visiting order, the reference Trotter neighbours, no "
+                         "world-line moves and one replica per word")
     orders = None
     if color is None:
         color, orders = _resolve_order(order, nbs, sched.size * int(mcsteps), int(nspins),
                                        int(seed) & 0xFFFFFFFF)
+    if carry:
+        if orders is None and not (isinstance(order, str) and order == "natural"):
+            raise ValueError("semantics='reference' needs order='natural', 'permutation' or explicit per-sweep orders")
+        per_word = 1
     import time
     t = [time.perf_counter()]
     d.set_graph(nbs, color)
@@ -206,8 +222,11 @@ def QuantumAnnealReplicas(sched, mcsteps, slices, temp, nspins, spins0, nbs, see
     t.append(time.perf_counter())
     d.set_global_moves(global_moves)
     try:
-        d.qa_colour(sched, int(mcsteps), temp, seed, replica0=replica0, trotter=TROTTER[trotter],
-                    orders=orders)
+        if carry:
+            d.qa_carry(sched, int(mcsteps), temp, seed, replica0=replica0, orders=orders)
+        else:
+            d.qa_colour(sched, int(mcsteps), temp, seed, replica0=replica0, trotter=TROTTER[trotter],
+                        orders=orders)
     finally:
         d.set_global_moves(False)
     t.append(time.perf_counter())

@@ -672,3 +672,51 @@ def test_energy_histogram_on_device(golden, dev):
         assert np.array_equal(h["counts"], ref.astype(np.uint64))
         assert h["below"] == int((v < lo).sum()) and h["above"] == int((v >= hi).sum())
         np.testing.assert_allclose([h["mean"], h["min"], h["max"]], [v.mean(), v.min(), v.max()], rtol=1e-12)
+
+
+# ------------------------------------------------------------ the as-shipped semantics at production speed
+@pytest.mark.parametrize("inst,P,T,R,mcsteps", [("inst_0_32x32", 20, 0.01, 5, 1), ("inst_0_32x32", 64, 0.3, 3, 2),
+                                               ("inst_0_32x32", 33, 0.05, 4, 1), ("hopfield8", 10, 0.2, 70, 3),
+                                               ("boixo", 2, 0.5, 9, 2), ("santoro_80x80", 20, 0.01, 2, 1)])
+def test_qa_carry_bit_exact(golden, dev, inst, P, T, R, mcsteps):
+    """piqmc_qa_carry (one warp per replica, the slices of a replica in lockstep over the visiting order, slice 1
+    first) == the CPU statement of the as-shipped loop nest (slices outermost, energy difference carried over a
+    slice sweep, piqmc/qmc.pyx:98-136), for permutation orders, the natural order, non-zero replica and sweep
+    offsets, P below and above 32."""
+    nbs, idx, J32, color = _graph(golden, inst)
+    n = NSPINS[inst]
+    sched = np.linspace(1.5, 1e-8, 5)
+    prng = np.random.RandomState(P)
+    for orders in (np.stack([prng.permutation(n) for _ in range(5 * mcsteps)]).astype(np.int32), None):
+        init = O.colour_init_spins(21, 6, R, n)
+        want = np.repeat(init[:, :, None], P, axis=2).copy()
+        O.qa_carry(sched, mcsteps, P, T, idx, J32, want, 21, replica0=6, sweep0=9, orders=orders)
+        dev.set_graph(nbs, color)
+        dev.state_alloc(R, P)
+        dev.state_init_random(21, 6, tile=True)
+        dev.qa_carry(sched, mcsteps, T, 21, replica0=6, sweep0=9, orders=orders)
+        got = np.transpose(tools.UnpackWords(dev.state_download_words(), P), (0, 2, 1))
+        assert np.array_equal(want, got)
+
+
+def test_qa_carry_residual_energy_distribution_vs_reference(golden, dev):
+    """Config 2 with the reference's DEFAULT function: 1024 runs of qmc.QuantumAnneal (as shipped: the energy
+    difference carried over a slice sweep; golden qa_100, made by the compiled reference) against 1024 replicas
+    of QuantumAnnealReplicas(semantics="reference", order="permutation") -- in 16 calls of 64 replicas with
+    their own seeds, because the replicas of one call share their permutations (every reference run draws its
+    own) and the residual depends on them a little.  KS p > 0.01 on the slice-averaged and the best-slice
+    residual energy per spin; and the carry statistics are far from the per-spin-reset ones (about 1.0 against
+    0.25 per spin)."""
+    import piqmc.qmc as qmc
+    nbs = golden["vec"]["nbs_inst_0_32x32"]
+    ref = golden["dist"]["qa_100"]
+    mine = np.concatenate([
+        qmc.QuantumAnnealReplicas(np.linspace(1.5, 1e-8, 100), 1, 20, 0.01, 1024, None, nbs, seed=4242 + 977 * b,
+                                  order="permutation", semantics="reference", nreplicas=64, replica0=64 * b,
+                                  device=dev)["energies"] for b in range(ref.shape[0] // 64)])
+    for name, a, b in (("mean", mine.mean(axis=1), ref.mean(axis=1)), ("best", mine.min(axis=1), ref.min(axis=1))):
+        p = ks_2samp_p(_residual(a, "inst_0_32x32"), _residual(b, "inst_0_32x32"))
+        print("as-shipped semantics, %s slice: residual/spin mine %.4f ref %.4f KS p %.3f"
+              % (name, _residual(a.mean(), "inst_0_32x32"), _residual(b.mean(), "inst_0_32x32"), p))
+        assert p > 0.01
+    assert _residual(mine.mean(), "inst_0_32x32") > 0.6
