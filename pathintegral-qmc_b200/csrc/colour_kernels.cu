@@ -404,16 +404,25 @@ __global__ void __launch_bounds__(128) resident_sweeps_int(
 // visited spin and its neighbours are warp-uniform loads; the flips of a step are collected by ballot.
 // Specification: oracle_qa_carry (oracle/piqmc_oracle.c part 4), bit for bit.
 // ------------------------------------------------------------------------------------------
+template <bool RESIDENT>
 __global__ void __launch_bounds__(256) qa_carry_kernel(
     uint64_t *__restrict__ words, int nspins, int nrows, int maxnb, const int32_t *__restrict__ idx,
     const float *__restrict__ J32, const int32_t *__restrict__ order, int per_sweep_orders, int nsweeps,
     const float *__restrict__ jp2s, const float *__restrict__ invTs, int lanes, uint32_t k0, uint32_t k1,
     uint32_t row0, uint32_t sweep0)
 {
+    extern __shared__ __align__(16) unsigned char rs_smem[];
     const int lane = threadIdx.x & 31;
     const int row = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (row >= nrows) return;                                  // whole warps
+    // RESIDENT: the replica's words live in shared memory for the whole run (8 N bytes per warp)
+    uint64_t *mine = reinterpret_cast<uint64_t *>(rs_smem) + (size_t)(threadIdx.x >> 5) * nspins;
     uint64_t *wrow = words + row;
+    if (RESIDENT) {
+        for (int i = lane; i < nspins; i += 32) mine[i] = wrow[(size_t)i * nrows];
+        __syncwarp();
+    }
+    const auto load = [&](int i) -> uint64_t { return RESIDENT ? mine[i] : __ldcg(wrow + (size_t)i * nrows); };
     const uint32_t prow = row0 + (uint32_t)row;
     const int top = lanes - 1;
     for (int s = 0; s < nsweeps; s++) {
@@ -424,15 +433,15 @@ __global__ void __launch_bounds__(256) qa_carry_kernel(
         float ed[2] = {0.0f, 0.0f};                            // the carries of slices lane, lane + 32
         for (int t = 0; t < nspins; t++) {
             const int i = ord ? __ldg(ord + t) : t;
-            const uint64_t w = __ldcg(wrow + (size_t)i * nrows);
+            const uint64_t w = load(i);
             // in-slice terms, table order
 #pragma unroll 1
             for (int n = 0; n < maxnb; n++) {
                 const int j = __ldg(idx + (size_t)i * maxnb + n);
                 const float negJ2 = -2.0f * __ldg(J32 + (size_t)i * maxnb + n);
-                const uint64_t x = (j == i) ? w : (w ^ __ldcg(wrow + (size_t)j * nrows));
+                const uint64_t x = (j == i) ? w : (w ^ load(j));
                 ed[0] = __fadd_rn(ed[0], flip_sign(negJ2, (uint32_t)(x >> lane) & 1u));
-                ed[1] = __fadd_rn(ed[1], flip_sign(negJ2, (uint32_t)(x >> (lane + 32)) & 1u));
+                if (lanes > 32) ed[1] = __fadd_rn(ed[1], flip_sign(negJ2, (uint32_t)(x >> (lane + 32)) & 1u));
             }
             const uint32_t old_top = (uint32_t)(w >> top) & 1u, old1 = (uint32_t)(w >> 1) & 1u;
             // the decision of slice k with the right-hand Trotter neighbour's bit `rb`: carries on, no reset
@@ -454,11 +463,16 @@ __global__ void __launch_bounds__(256) qa_carry_kernel(
             const uint32_t new1 = old1 ^ (uint32_t)__shfl_sync(0xffffffffu, (int)f0, 1);
             if (lane != 1 && lane < lanes) f0 = decide(lane, 0, lane == 0 ? old1 : new1);
             if (lane + 32 < lanes) f1 = decide(lane + 32, 1, new1);
-            const uint32_t lo = __ballot_sync(0xffffffffu, f0), hi = __ballot_sync(0xffffffffu, f1);
-            if (lane == 0) wrow[(size_t)i * nrows] = w ^ (((uint64_t)hi << 32) | lo);
+            const uint32_t lo = __ballot_sync(0xffffffffu, f0), hi = lanes > 32 ? __ballot_sync(0xffffffffu, f1) : 0u;
+            if (lane == 0) {
+                if (RESIDENT) mine[i] = w ^ (((uint64_t)hi << 32) | lo);
+                else wrow[(size_t)i * nrows] = w ^ (((uint64_t)hi << 32) | lo);
+            }
             __syncwarp();
         }
     }
+    if (RESIDENT)
+        for (int i = lane; i < nspins; i += 32) wrow[(size_t)i * nrows] = mine[i];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -667,10 +681,22 @@ int launch_qa_carry(piqmc_ctx *c, const int32_t *d_order, int per_sweep_orders, 
                     const float *d_invT, uint64_t seed, uint32_t row0, uint32_t sweep0)
 {
     if (nsweeps <= 0) return PIQMC_OK;
-    const int wpb = 8;
-    qa_carry_kernel<<<(unsigned)((c->nrows + wpb - 1) / wpb), wpb * 32, 0, c->stream>>>(
-        c->d_words, c->nspins, c->nrows, c->maxnb, c->d_idx, c->d_J32, d_order, per_sweep_orders, nsweeps, d_jp2, d_invT,
-        c->lanes, (uint32_t)seed, (uint32_t)(seed >> 32), row0, sweep0);
+    // the words of a replica in shared memory when at least one warp's worth fits (as many warps per block as fit, 8 at most)
+    // (measured: with fewer than 8 warps per block the kernel is latency-bound and slower than reading through L2)
+    int wpb = (int)std::min<size_t>(8, (size_t)(160 * 1024) / ((size_t)c->nspins * 8));
+    if (getenv("PIQMC_CARRY_GLOBAL")) wpb = 0;
+    if (wpb >= 8 || (wpb >= 1 && getenv("PIQMC_CARRY_RESIDENT"))) {
+        const size_t smem = (size_t)wpb * c->nspins * 8;
+        PIQMC_CUDA(cudaFuncSetAttribute((const void *)qa_carry_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        qa_carry_kernel<true><<<(unsigned)((c->nrows + wpb - 1) / wpb), wpb * 32, smem, c->stream>>>(
+            c->d_words, c->nspins, c->nrows, c->maxnb, c->d_idx, c->d_J32, d_order, per_sweep_orders, nsweeps, d_jp2, d_invT,
+            c->lanes, (uint32_t)seed, (uint32_t)(seed >> 32), row0, sweep0);
+    } else {
+        wpb = 8;
+        qa_carry_kernel<false><<<(unsigned)((c->nrows + wpb - 1) / wpb), wpb * 32, 0, c->stream>>>(
+            c->d_words, c->nspins, c->nrows, c->maxnb, c->d_idx, c->d_J32, d_order, per_sweep_orders, nsweeps, d_jp2, d_invT,
+            c->lanes, (uint32_t)seed, (uint32_t)(seed >> 32), row0, sweep0);
+    }
     c->launches++;
     PIQMC_CUDA(cudaGetLastError());
     return PIQMC_OK;

@@ -693,10 +693,16 @@ def test_qa_carry_bit_exact(golden, dev, inst, P, T, R, mcsteps):
         O.qa_carry(sched, mcsteps, P, T, idx, J32, want, 21, replica0=6, sweep0=9, orders=orders)
         dev.set_graph(nbs, color)
         dev.state_alloc(R, P)
-        dev.state_init_random(21, 6, tile=True)
-        dev.qa_carry(sched, mcsteps, T, 21, replica0=6, sweep0=9, orders=orders)
-        got = np.transpose(tools.UnpackWords(dev.state_download_words(), P), (0, 2, 1))
-        assert np.array_equal(want, got)
+        for env in ({"PIQMC_CARRY_RESIDENT": "1"}, {"PIQMC_CARRY_GLOBAL": "1"}):   # words in shared memory | read through L2
+            os.environ.update(env)
+            try:
+                dev.state_init_random(21, 6, tile=True)
+                dev.qa_carry(sched, mcsteps, T, 21, replica0=6, sweep0=9, orders=orders)
+            finally:
+                for k in env:
+                    del os.environ[k]
+            got = np.transpose(tools.UnpackWords(dev.state_download_words(), P), (0, 2, 1))
+            assert np.array_equal(want, got)
 
 
 def test_qa_carry_residual_energy_distribution_vs_reference(golden, dev):
