@@ -21,3 +21,10 @@ out = qmc.QuantumAnnealReplicas(np.linspace(1.5, 1e-8, 100), 1, P, T, nspins, "r
 best = out["energies"].min(axis=1)
 print("QA  residual energy per spin: %.4f (slice mean), %.4f (best slice)"
       % ((out["energies"].mean() - gs_energy) / nspins, (best.mean() - gs_energy) / nspins))
+
+# The reference's default function (qmc.QuantumAnneal, what examples/spinglass32.py of the reference calls)
+# carries its energy difference over a whole slice sweep (qmc.pyx:134-135); semantics="reference" runs exactly
+# that rule, a fresh permutation per sweep, from the same kind of random start -- markedly different statistics.
+ref = qmc.QuantumAnnealReplicas(np.linspace(1.5, 1e-8, 100), 1, P, T, nspins, None, neighbors, seed=3,
+                                order="permutation", semantics="reference", nreplicas=R)
+print("QA, as-shipped rule: residual energy per spin %.4f (slice mean)" % ((ref["energies"].mean() - gs_energy) / nspins))
