@@ -4,6 +4,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 #include <new>
@@ -514,6 +515,143 @@ static int check_orders(int nspins, size_t nsweeps, const int32_t *orders)
 }
 
 // Sweeps driver shared by QA and SA.  value[f] is jp2 (QA) or unused; invT[f] per schedule step.
+// ---- anneal + results in one call: the host side of the staggered launch ------------------------------
+// Streams, the per-chunk counters and the mapped flags; everything is allocated BEFORE the sweep kernel is
+// launched (an allocation would wait for it).
+static int pipe_prepare(piqmc_ctx *h, int nchunks)
+{
+    if (!h->copy_stream) PIQMC_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    if (!h->copy_event) PIQMC_CUDA(cudaEventCreateWithFlags(&h->copy_event, cudaEventDisableTiming));
+    if (!h->aux_stream) {
+        int lo = 0, hi = 0;
+        PIQMC_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));      // hi = numerically lowest = greatest priority
+        PIQMC_CUDA(cudaStreamCreateWithPriority(&h->aux_stream, cudaStreamNonBlocking, hi));
+    }
+    if (!h->aux_event) PIQMC_CUDA(cudaEventCreateWithFlags(&h->aux_event, cudaEventDisableTiming));
+    if (nchunks > h->pipe_chunk_cap) {
+        PIQMC_CUDA(cudaStreamSynchronize(h->stream));
+        free_dev(h->d_chunk_count);
+        if (h->h_chunk_flag) cudaFreeHost(h->h_chunk_flag);
+        h->h_chunk_flag = h->d_chunk_flag = nullptr;
+        h->pipe_chunk_cap = 0;
+        const int cap = std::max(64, nchunks);
+        PIQMC_CUDA(cudaMalloc(&h->d_chunk_count, cap * sizeof(unsigned int)));
+        PIQMC_CUDA(cudaHostAlloc((void **)&h->h_chunk_flag, cap * sizeof(unsigned int), cudaHostAllocMapped | cudaHostAllocPortable));
+        PIQMC_CUDA(cudaHostGetDevicePointer((void **)&h->d_chunk_flag, h->h_chunk_flag, 0));
+        h->pipe_chunk_cap = cap;
+    }
+    PIQMC_CUDA(cudaMemsetAsync(h->d_chunk_count, 0, nchunks * sizeof(unsigned int), h->stream));
+    for (int c = 0; c < nchunks; c++) h->h_chunk_flag[c] = 0u;
+    __sync_synchronize();
+    return energy_reserve(h);
+}
+
+// Stagger between consecutive row chunks: they should finish at the rate the host link takes them (one chunk's
+// download per stagger), but the ramps at both ends of the run stay a fraction of it.  Measured on B200
+// (profiles/r2_e2e_overlap.md): a ticket period with few active rows is bound by its dependency chain and costs
+// as much as the download it hides (256x256 torus: 1.8 ms per period with one 512-row chunk active, 3.6 ms with
+// all 4096 rows), so staggering only pays when the ramps still hold thousands of rows: states of 16384+ rows.
+static int pipe_choose_lag16(const piqmc_ctx *h, size_t nsweeps, int rpb, int nchunks)
+{
+    if (const char *e = getenv("PIQMC_PIPE_LAG16")) return std::max(0, atoi(e));
+    if (nchunks < 2 || h->nrows < 16384) return 0;
+    const double t_copy = (double)rpb * h->nspins * 8.0 / 43e9;                         // one chunk over the host link, GPU busy
+    const double levels = (double)std::max(1, h->ncolors) / (double)(h->flow_extra + 1);
+    const double t_period = std::max((double)h->nrows * h->nspins * 64.0 / 4.5e12,     // issue-bound sweep ...
+                                     levels * 3.9e-6);                                 // ... or its dependency chain
+    double lag = t_copy / t_period;
+    lag = std::min(lag, 0.5 * (double)nsweeps / (double)(nchunks - 1));
+    return (int)(lag * 16.0 + 0.5);
+}
+
+// Called between the launch of the staggered sweeps and the stream synchronisation: takes the chunks in the
+// order they finish, downloads each (copy engine) and reduces its energies (high-priority stream) while the
+// rest of the launch is still running.
+static int pipe_drain(piqmc_ctx *h)
+{
+    const int rpb = fast_chunk_rows(h);
+    const int nchunks = (h->nrows + rpb - 1) / rpb;
+    volatile unsigned int *flag = h->h_chunk_flag;
+    bool kernel_over = false;
+    // PIQMC_PIPE_TRACE=1: when each chunk was seen final, and when its download and its energy reduction ran
+    // (milliseconds since the drain began), on stderr.  The energies are reduced once, behind the sweeps and under
+    // the tail of the downloads (PIQMC_PIPE_ENERGY=chunk: per chunk on a high-priority stream instead -- measured:
+    // those launches only start when the queued downloads have drained, profiles/r2_e2e_overlap.md)
+    const bool trace = getenv("PIQMC_PIPE_TRACE") != nullptr && nchunks <= 64;
+    const char *een = getenv("PIQMC_PIPE_ENERGY");
+    const bool energy_at_end = !(een != nullptr && een[0] == 'c');
+    std::vector<cudaEvent_t> ev;
+    std::vector<double> seen(nchunks, 0.0);
+    struct timespec ts0;
+    clock_gettime(CLOCK_MONOTONIC, &ts0);
+    auto now_ms = [&]() {
+        struct timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return 1e3 * (double)(ts.tv_sec - ts0.tv_sec) + 1e-6 * (double)(ts.tv_nsec - ts0.tv_nsec);
+    };
+    if (trace) {
+        ev.resize(1 + 4 * (size_t)nchunks);
+        for (auto &e : ev) PIQMC_CUDA(cudaEventCreate(&e));
+        PIQMC_CUDA(cudaEventRecord(ev[0], h->copy_stream));
+    }
+    for (int c = 0; c < nchunks; c++) {
+        unsigned int spins = 0;
+        while (!kernel_over && flag[c] == 0u) {
+            if ((++spins & 0x3FFu) == 0u) {
+                const cudaError_t q = cudaStreamQuery(h->stream);
+                if (q == cudaSuccess) kernel_over = true;          // every flag has been written (or the watchdog fired)
+                else if (q != cudaErrorNotReady) {
+                    piqmc_set_error("dataflow sweeps failed: %s", cudaGetErrorString(q));
+                    return PIQMC_ECUDA;
+                }
+            }
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
+        __sync_synchronize();
+        if (trace) seen[c] = now_ms();
+        const int row_lo = c * rpb, cnt = std::min(rpb, h->nrows - row_lo);
+        if (trace) PIQMC_CUDA(cudaEventRecord(ev[1 + 4 * c], h->copy_stream));
+        PIQMC_CUDA(cudaMemcpy2DAsync(h->pipe_words + row_lo, (size_t)h->nrows * sizeof(uint64_t), h->d_words + row_lo,
+                                     (size_t)h->nrows * sizeof(uint64_t), (size_t)cnt * sizeof(uint64_t), h->nspins,
+                                     cudaMemcpyDeviceToHost, h->copy_stream));
+        if (trace) PIQMC_CUDA(cudaEventRecord(ev[2 + 4 * c], h->copy_stream));
+        if (energy_at_end) continue;
+        if (trace) PIQMC_CUDA(cudaEventRecord(ev[3 + 4 * c], h->aux_stream));
+        TRY(launch_energy_rows(h, row_lo, cnt, h->aux_stream));
+        if (trace) PIQMC_CUDA(cudaEventRecord(ev[4 + 4 * c], h->aux_stream));
+    }
+    PIQMC_CUDA(cudaStreamSynchronize(h->stream));
+    const double t_sweeps = now_ms();
+    cudaStream_t es = energy_at_end ? h->stream : h->aux_stream;
+    if (energy_at_end) TRY(launch_energy_rows(h, 0, h->nrows, es));
+    // one download of all energies (small) behind the last reduction
+    PIQMC_CUDA(cudaMemcpyAsync(h->pipe_energies, h->d_energy, (size_t)h->nrows * h->lanes * sizeof(double),
+                               cudaMemcpyDeviceToHost, es));
+    PIQMC_CUDA(cudaStreamSynchronize(es));
+    const double t_energy = now_ms();
+    PIQMC_CUDA(cudaStreamSynchronize(h->copy_stream));
+    if (trace) {
+        fprintf(stderr, "[piqmc pipe] %d chunks of %d rows, lag16 %d: sweeps over at %.2f ms, energies at %.2f, downloads at %.2f\n",
+                nchunks, rpb, h->pipe_lag16, t_sweeps, t_energy, now_ms());
+        for (int c = 0; c < nchunks; c++) {
+            float a = 0, b = 0, e0 = 0, e1 = 0;
+            cudaEventElapsedTime(&a, ev[0], ev[1 + 4 * c]);
+            cudaEventElapsedTime(&b, ev[0], ev[2 + 4 * c]);
+            if (!energy_at_end) {
+                cudaEventElapsedTime(&e0, ev[0], ev[3 + 4 * c]);
+                cudaEventElapsedTime(&e1, ev[0], ev[4 + 4 * c]);
+            }
+            fprintf(stderr, "[piqmc pipe]   chunk %d final at %.2f ms; download %.2f -> %.2f; energy %.2f -> %.2f\n", c,
+                    seen[c], a, b, e0, e1);
+        }
+        for (auto &e : ev) cudaEventDestroy(e);
+    }
+    h->pipe_runs++;
+    return PIQMC_OK;
+}
+
 static int run_colour_sweeps(piqmc_ctx *h, int qa, int trotter, int nsched, int mcsteps,
                              const std::vector<float> &jp2, const std::vector<float> &invT, uint64_t seed,
                              uint32_t row0, uint32_t sweep0, const int32_t *orders)
@@ -581,8 +719,17 @@ static int run_colour_sweeps(piqmc_ctx *h, int qa, int trotter, int nsched, int 
         return launch_chain_sweeps(h, qa, nsched, mcsteps, jp2.data(), invT.data(), seed, row0, sweep0);
     if (!orders) {
         if (fast) {
+            if (h->pipe_request) {
+                const int rpb = fast_chunk_rows(h);
+                const int nchunks = (h->nrows + rpb - 1) / rpb;
+                h->pipe_lag16 = pipe_choose_lag16(h, nsweeps, rpb, nchunks);
+                // no stagger, no overlap: the plain sequence (one contiguous download under the energy reduction) is faster
+                if (nchunks <= 255 && (h->pipe_lag16 > 0 || getenv("PIQMC_PIPE_LAG16"))) TRY(pipe_prepare(h, nchunks));
+                else h->pipe_request = 0;
+            }
             TRY(launch_fast_sweeps(h, qa, trotter, (int)nsweeps, h->d_recs, h->flow_extra, 0, d_jp2.p, d_invT.p, seed,
                                    row0, sweep0));
+            if (h->pipe_armed) TRY(pipe_drain(h));
             // the per-sweep parameter arrays must outlive the launch
             PIQMC_CUDA(cudaStreamSynchronize(h->stream));
             return piqmc_check_watchdog(h, "dataflow sweeps");
@@ -730,6 +877,10 @@ int piqmc_destroy(piqmc_handle h)
     free_dev(h->d_cband);
     free_dev(h->d_cprog);
     free_dev(h->d_cll);
+    free_dev(h->d_chunk_count);
+    if (h->h_chunk_flag) cudaFreeHost(h->h_chunk_flag);
+    if (h->aux_event) cudaEventDestroy(h->aux_event);
+    if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
     if (h->copy_event) cudaEventDestroy(h->copy_event);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     cudaStreamDestroy(h->stream);
@@ -1376,6 +1527,31 @@ int piqmc_qa_colour(piqmc_handle h, const double *sched, int nsched, int mcsteps
     for (int f = 0; f < nsched; f++) jp2[f] = 2.0f * piqmc_jperp(sched[f], slices, temp);
     return run_colour_sweeps(h, 1, trotter, nsched, mcsteps, jp2, invT, seed, replica0, sweep0, orders);
 }
+
+// Anneal, energies and download in one call.  With the dataflow kernel and a static colouring the row chunks
+// of the launch are staggered and downloaded as they finish (pipe_drain); every other configuration runs the
+// three steps one after the other.  Same results either way.
+int piqmc_qa_colour_results(piqmc_handle h, const double *sched, int nsched, int mcsteps, float temp, uint64_t seed,
+                            uint32_t replica0, uint32_t sweep0, int trotter, const int32_t *orders, double *energies,
+                            uint64_t *words)
+{
+    USE(h);
+    PIQMC_REQUIRE(energies && words, PIQMC_EINVAL, "null output");
+    h->pipe_armed = 0;
+    h->pipe_request = 1;
+    if (const char *e = getenv("PIQMC_PIPE")) h->pipe_request = atoi(e) != 0;
+    h->pipe_energies = energies;
+    h->pipe_words = words;
+    const int rc = piqmc_qa_colour(h, sched, nsched, mcsteps, temp, seed, replica0, sweep0, trotter, orders);
+    const bool done = h->pipe_armed != 0;
+    h->pipe_request = h->pipe_armed = 0;
+    h->pipe_energies = nullptr;
+    h->pipe_words = nullptr;
+    if (rc != PIQMC_OK) return rc;
+    return done ? PIQMC_OK : piqmc_results(h, energies, words);
+}
+
+uint64_t piqmc_pipelined_runs(piqmc_handle h) { return h ? h->pipe_runs : 0; }
 
 int piqmc_qa_carry(piqmc_handle h, const double *sched, int nsched, int mcsteps, float temp, uint64_t seed,
                    uint32_t replica0, uint32_t sweep0, const int32_t *orders)

@@ -26,6 +26,8 @@
 
 namespace {
 
+constexpr int FAST_MAX_LAG = 32;     // largest stagger of the last chunk, in ticket periods
+
 struct FastArgs {
     uint64_t *words;            // [N][nrows]
     const PiqmcUnitRec *recs;   // per sweep (or shared): one record per member, in ticket order
@@ -47,6 +49,19 @@ struct FastArgs {
     // every segment, and of one whole segment
     int seg_P, seg_S;
     uint64_t seg_low, seg_l1, seg_top, seg_ones;
+    // staggered row chunks (piqmc_qa_colour_results): chunk c runs (c * lag16) / 16 ticket periods behind chunk 0,
+    // so the chunks finish one after the other and the host downloads each while the others still sweep.
+    // Row chunks never interact, so any stagger leaves the result and the topological ticket order intact.
+    // Chunk c is active in the ticket periods [lag(c), lag(c) + nper), nper = sweeps + ramp periods of the colouring;
+    // only active (period, chunk) pairs get tickets.  With lmax = lag(last chunk) <= nper the periods fall into a
+    // ramp-up [0, lmax) (chunks 0 .. nact_up[q] - 1), a steady part [lmax, nper) (all chunks) and a ramp-down
+    // [nper, nper + lmax) (chunks clo_dn[q - nper] .. nchunks - 1); pref_* = first ticket of each ramp period.
+    int lag16, lmax, nper;
+    unsigned int base_steady, base_down;
+    unsigned int pref_up[FAST_MAX_LAG + 1], pref_dn[FAST_MAX_LAG + 1];
+    unsigned char nact_up[FAST_MAX_LAG + 1], clo_dn[FAST_MAX_LAG + 1];
+    unsigned int *chunk_count;  // [nchunks] units of the launch's last sweep that have finished (null: no signal)
+    unsigned int *chunk_flag;   // [nchunks] mapped host memory: set when a chunk has finished all its sweeps
 };
 
 // MINB = resident blocks per SM the register allocation is capped for (7 -> 72 registers, 8 -> 64, 9 -> 56):
@@ -68,11 +83,28 @@ __global__ void __launch_bounds__(FAST_THREADS, MINB) colour_sweep_fast(const Fa
     if (threadIdx.x == 0) {                      // one thread takes and decodes the ticket for the block
         const unsigned int t = atomicAdd(a.ticket, 1u) - a.ticket_base;
         const unsigned int per_sweep = (unsigned int)a.nspins * (unsigned int)a.nchunks;
-        const unsigned int q = t / per_sweep;
-        const unsigned int rem = t - q * per_sweep;
-        const unsigned int m = rem / (unsigned int)a.nchunks;
+        unsigned int q, rem, nact = (unsigned int)a.nchunks, clo = 0u;
+        if (t >= a.base_steady && t < a.base_down) {              // all chunks active (every ticket when lag16 == 0)
+            const unsigned int u = t - a.base_steady;
+            q = u / per_sweep;
+            rem = u - q * per_sweep;
+            q += (unsigned int)a.lmax;
+        } else if (t < a.base_steady) {                            // ramp-up: the first nact_up[q] chunks
+            q = 0u;
+            while (a.pref_up[q + 1] <= t) q++;
+            rem = t - a.pref_up[q];
+            nact = a.nact_up[q];
+        } else {                                                   // ramp-down: chunks clo_dn[j] and up
+            unsigned int j = 0u;
+            while (a.pref_dn[j + 1] <= t) j++;
+            rem = t - a.pref_dn[j];
+            clo = a.clo_dn[j];
+            nact -= clo;
+            q = (unsigned int)a.nper + j;
+        }
+        const unsigned int m = rem / nact;
         s_unit[0] = (int)q;
-        s_unit[1] = (int)(rem - m * (unsigned int)a.nchunks);
+        s_unit[1] = (int)(clo + rem - m * nact);
         s_unit[2] = (int)m;
     }
     __syncthreads();
@@ -83,7 +115,7 @@ __global__ void __launch_bounds__(FAST_THREADS, MINB) colour_sweep_fast(const Fa
     const int4 *rp = reinterpret_cast<const int4 *>(a.recs + (a.per_sweep_lists ? (size_t)q * a.nspins : 0) + m);
     const int4 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2);
     const int i = r0.x;
-    const int s = q - r0.y;
+    const int s = q - r0.y - ((chunk * a.lag16) >> 4);
     if (s < 0 || s >= a.nsweeps) return;                           // ramp-up / ramp-down periods
     const int nb[4] = {r0.z, r0.w, r1.x, r1.y};
     const float Jn[4] = {__int_as_float(r1.z), __int_as_float(r1.w), __int_as_float(r2.x), __int_as_float(r2.y)};
@@ -354,8 +386,19 @@ __global__ void __launch_bounds__(FAST_THREADS, MINB) colour_sweep_fast(const Fa
 
     // ---- publish: all stores of the block happen-before the flag
     __syncthreads();
-    if (threadIdx.x == 0)                                           // release orders the block's stores
+    if (threadIdx.x == 0) {                                         // release orders the block's stores
         st_release(a.done + (size_t)i * a.nchunks + chunk, tag);   // (cumulative through the barrier)
+        if (a.chunk_count != nullptr && tag == a.tag0 + (uint32_t)a.nsweeps) {
+            // last sweep of the launch: count the spins of this row chunk that are final; the unit that completes
+            // the chunk tells the host (fence; atomic = release, atomic; fence = acquire, both system-wide: the
+            // copy engine then reads final words)
+            __threadfence_system();
+            if (atomicAdd(a.chunk_count + chunk, 1u) == (unsigned int)a.nspins - 1u) {
+                __threadfence_system();
+                *(volatile unsigned int *)(a.chunk_flag + chunk) = 1u;
+            }
+        }
+    }
 }
 
 }  // namespace
@@ -377,6 +420,8 @@ static int fast_rows_per_block(const piqmc_ctx *c)
 // One launch holds (sweeps + ramp periods) * N * chunks units; the ticket arithmetic is 32-bit and a
 // grid has at most 2^31 - 1 blocks.  A colouring with many levels and a small level gap (a path graph
 // in natural order) can exceed that even for one sweep: the caller then takes another kernel.
+int fast_chunk_rows(const piqmc_ctx *c) { return fast_rows_per_block(c); }
+
 bool launch_fast_fits(const piqmc_ctx *c, int nperiods_extra)
 {
     const int rpb = fast_rows_per_block(c);
@@ -452,6 +497,21 @@ int launch_fast_sweeps(piqmc_ctx *c, int qa, int trotter, int nsweeps, const Piq
                   "colouring with %d ramp periods x %zu units per sweep does not fit one launch of the dataflow kernel",
                   nperiods_extra, per_sweep);
     const int max_sweeps = (int)std::max<long long>(1, (long long)(((size_t)1 << 30) / per_sweep) - nperiods_extra);
+    // staggered chunks with a completion signal per chunk: only when the run is one launch
+    a.lag16 = 0;
+    a.chunk_count = nullptr;
+    a.chunk_flag = nullptr;
+    c->pipe_armed = 0;
+    if (c->pipe_request && nchunks <= c->pipe_chunk_cap && nchunks <= 255 && nsweeps <= max_sweeps) {
+        // the stagger of the last chunk stays within the table size and within the periods of one chunk
+        int lag16 = c->pipe_lag16;
+        const int cap = std::min(FAST_MAX_LAG, nsweeps + nperiods_extra);
+        if (nchunks > 1 && (((nchunks - 1) * lag16) >> 4) > cap) lag16 = (cap << 4) / (nchunks - 1);
+        a.lag16 = c->pipe_lag16 = lag16;
+        a.chunk_count = c->d_chunk_count;
+        a.chunk_flag = c->d_chunk_flag;
+        c->pipe_armed = 1;
+    }
     unsigned int ticket_base = 0;
     for (int s0 = 0; s0 < nsweeps; s0 += max_sweeps) {
         const int ns = std::min(max_sweeps, nsweeps - s0);
@@ -462,7 +522,34 @@ int launch_fast_sweeps(piqmc_ctx *c, int qa, int trotter, int nsweeps, const Piq
         a.sweep0 = sweep0 + (uint32_t)s0;
         a.tag0 = c->flow_tag + (uint32_t)s0;
         a.ticket_base = ticket_base;
-        const size_t nunits = (size_t)(ns + nperiods_extra) * per_sweep;
+        const size_t nunits = (size_t)(ns + nperiods_extra) * per_sweep;   // staggered or not: active pairs only
+        // ticket -> (period, chunk) tables of the stagger (trivial when lag16 == 0)
+        a.nper = ns + nperiods_extra;
+        a.lmax = ((nchunks - 1) * a.lag16) >> 4;
+        {
+            unsigned int acc = 0;
+            for (int q = 0; q <= a.lmax; q++) {                  // ramp-up: chunks with lag <= q
+                int nact = 0;
+                while (nact < nchunks && ((nact * a.lag16) >> 4) <= q) nact++;
+                a.pref_up[q] = acc;
+                a.nact_up[q] = (unsigned char)nact;
+                if (q < a.lmax) acc += (unsigned int)c->nspins * (unsigned int)nact;
+            }
+            a.base_steady = acc;
+            acc += (unsigned int)(a.nper - a.lmax) * (unsigned int)per_sweep;
+            a.base_down = acc;
+            for (int j = 0; j <= a.lmax; j++) {                  // ramp-down: chunks with lag + nper > nper + j
+                int clo = 0;
+                while (clo < nchunks && ((clo * a.lag16) >> 4) <= j) clo++;
+                a.pref_dn[j] = acc;
+                a.clo_dn[j] = (unsigned char)clo;
+                if (j < a.lmax) acc += (unsigned int)c->nspins * (unsigned int)(nchunks - clo);
+            }
+            if (acc != (unsigned int)nunits) {
+                piqmc_set_error("internal: stagger tables cover %u tickets, grid has %zu", acc, nunits);
+                return PIQMC_EINVAL;
+            }
+        }
         ticket_base += (unsigned int)nunits;
         dim3 block(FAST_THREADS), grid((unsigned)nunits);
         int minb = (qa && !trotter) ? 9 : 8;      // measured on B200: 9 blocks/SM (56 registers) best from 512 to 4096 rows

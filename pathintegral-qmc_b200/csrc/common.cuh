@@ -163,6 +163,21 @@ struct piqmc_ctx {
 
     int variant = 0;
     int global_moves = 0;           // QA world-line moves (fast kernel only)
+
+    // anneal + results in one call (piqmc_qa_colour_results): the row chunks of the dataflow launch are
+    // staggered and tell the host when they are final; it downloads them while the others still sweep
+    int pipe_request = 0;           // set around the launch by piqmc_qa_colour_results
+    int pipe_lag16 = 0;             // stagger between consecutive chunks, 1/16 ticket periods
+    int pipe_armed = 0;             // launch_fast_sweeps took the request (one launch, few enough chunks)
+    int pipe_chunk_cap = 0;         // entries of the two arrays below
+    unsigned int *d_chunk_count = nullptr;
+    unsigned int *h_chunk_flag = nullptr;   // cudaHostAlloc (mapped)
+    unsigned int *d_chunk_flag = nullptr;   // its device alias
+    cudaStream_t aux_stream = nullptr;      // high priority: per-chunk energy reductions next to the running sweeps
+    cudaEvent_t aux_event = nullptr;
+    uint64_t pipe_runs = 0;         // calls that went through the pipelined path (reported to tests / bench)
+    double *pipe_energies = nullptr;        // host destinations of the call in flight
+    uint64_t *pipe_words = nullptr;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -245,6 +260,10 @@ int resident_rows_per_block(const piqmc_ctx *c, int qa);
 int launch_qa_carry(piqmc_ctx *c, const int32_t *d_order, int per_sweep_orders, int nsweeps, const float *d_jp2,
                     const float *d_invT, uint64_t seed, uint32_t row0, uint32_t sweep0);
 int launch_energy(piqmc_ctx *c);
+// rows [row_lo, row_lo + count) only, on `stream`; the scratch must have been sized by energy_reserve
+int energy_reserve(piqmc_ctx *c);
+int launch_energy_rows(piqmc_ctx *c, int row_lo, int count, cudaStream_t stream);
+int fast_chunk_rows(const piqmc_ctx *c);   // rows per unit of the dataflow kernel for the current state
 int launch_energy_histogram(piqmc_ctx *c, int reduce, double e0, double scale, double lo, double hi, int nbins,
                             unsigned long long *d_counts, double *d_stats);
 int launch_energy_coo(piqmc_ctx *c, int nspins, int nnz, const int32_t *d_row, const int32_t *d_col,

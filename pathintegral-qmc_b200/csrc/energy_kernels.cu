@@ -21,11 +21,11 @@ constexpr int EN_THREADS = 256;
 // thread, one per lane.  Fields and bonds go into the same sum: E = -(sum).
 __global__ void __launch_bounds__(EN_THREADS) energy_partial_kernel(
     const uint64_t *__restrict__ words, int nspins, int nrows, int maxnb,
-    const int32_t *__restrict__ idx, const double *__restrict__ J, double *__restrict__ part)
+    const int32_t *__restrict__ idx, const double *__restrict__ J, double *__restrict__ part, int row_lo, int row_hi)
 {
     const int lg = threadIdx.x & 7;
-    const int row = blockIdx.x * EN_ROWS + (threadIdx.x >> 3);
-    const bool live = row < nrows;
+    const int row = row_lo + blockIdx.x * EN_ROWS + (threadIdx.x >> 3);
+    const bool live = row < row_hi;
     const uint64_t *wrow = words + (live ? row : 0);   // word of spin s at wrow[s*nrows]
     double acc[8];
 #pragma unroll
@@ -51,10 +51,10 @@ __global__ void __launch_bounds__(EN_THREADS) energy_partial_kernel(
 }
 
 __global__ void energy_final_kernel(const double *__restrict__ part, int nsplit, int nrows, int lanes,
-                                    double *__restrict__ out)
+                                    double *__restrict__ out, int row_lo, int row_hi)
 {
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= nrows * lanes) return;
+    const int tid = row_lo * lanes + blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= row_hi * lanes) return;
     const int row = tid / lanes, lane = tid % lanes;
     double q = 0.0;
     for (int b = 0; b < nsplit; b++) q += part[((size_t)b * nrows + row) * 64 + lane];   // fixed order
@@ -146,30 +146,46 @@ int launch_energy_histogram(piqmc_ctx *c, int reduce, double e0, double scale, d
     return PIQMC_OK;
 }
 
-int launch_energy(piqmc_ctx *c)
+// the split of the spin sum depends on the graph only, never on the number of rows (nor on the row range of
+// a launch): a replica's energy is the same float64 whichever shard of the replicas it is computed in
+static int energy_nsplit(const piqmc_ctx *c) { return std::max(1, std::min(64, (c->nspins + 63) / 64)); }
+
+int energy_reserve(piqmc_ctx *c)
 {
-    const int tiles = (c->nrows + EN_ROWS - 1) / EN_ROWS;
-    // the split of the spin sum depends on the graph only, never on the number of rows: a replica's
-    // energy is the same float64 whichever shard of the replicas it is computed in
-    const int nsplit = std::max(1, std::min(64, (c->nspins + 63) / 64));
-    const size_t need = (size_t)nsplit * c->nrows * 64;
+    const size_t need = (size_t)energy_nsplit(c) * c->nrows * 64;
     if (need > c->epart_elems) {
         if (c->d_epart) PIQMC_CUDA(cudaFree(c->d_epart));
         c->d_epart = nullptr;
+        c->epart_elems = 0;
         PIQMC_CUDA(cudaMalloc(&c->d_epart, need * sizeof(double)));
         c->epart_elems = need;
     }
+    return PIQMC_OK;
+}
+
+int launch_energy_rows(piqmc_ctx *c, int row_lo, int count, cudaStream_t stream)
+{
+    if (count <= 0) return PIQMC_OK;
+    const int tiles = (count + EN_ROWS - 1) / EN_ROWS;
+    const int nsplit = energy_nsplit(c);
     dim3 grid(tiles, nsplit);
-    energy_partial_kernel<<<grid, EN_THREADS, 0, c->stream>>>(c->d_words, c->nspins, c->nrows, c->maxnb, c->d_idx,
-                                                             c->d_J64, c->d_epart);
+    energy_partial_kernel<<<grid, EN_THREADS, 0, stream>>>(c->d_words, c->nspins, c->nrows, c->maxnb, c->d_idx,
+                                                          c->d_J64, c->d_epart, row_lo, row_lo + count);
     c->launches++;
     PIQMC_CUDA(cudaGetLastError());
-    const int n = c->nrows * c->lanes;
-    energy_final_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_epart, nsplit, c->nrows, c->lanes,
-                                                               c->d_energy);
+    const int n = count * c->lanes;
+    energy_final_kernel<<<(n + 255) / 256, 256, 0, stream>>>(c->d_epart, nsplit, c->nrows, c->lanes, c->d_energy,
+                                                            row_lo, row_lo + count);
     c->launches++;
     PIQMC_CUDA(cudaGetLastError());
     return PIQMC_OK;
+}
+
+int launch_energy(piqmc_ctx *c)
+{
+    int rc = energy_reserve(c);
+    if (rc != PIQMC_OK) return rc;
+    return launch_energy_rows(c, 0, c->nrows, c->stream);
 }
 
 int launch_energy_coo(piqmc_ctx *c, int nspins, int nnz, const int32_t *d_row, const int32_t *d_col,

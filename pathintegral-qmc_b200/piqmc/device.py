@@ -111,6 +111,16 @@ class Device:
     def set_graph(self, nbs, color=None):
         """Upload the neighbour table (and, for the colour paths, a proper colouring).
         Cached on content: re-uploading the same table is free."""
+        # the same table and colouring as last time (the usual case for repeated anneals of one instance): an exact
+        # comparison with the private copies kept below, a fraction of a millisecond, instead of casts + a digest
+        last = getattr(self, "_graph_last", None)
+        if last is not None and self._graph_key is not None:
+            nbs_l, col_l = last
+            a = np.asarray(nbs)
+            if (a.shape == nbs_l.shape and a.dtype == nbs_l.dtype and (color is None) == (col_l is None)
+                    and np.array_equal(a, nbs_l)
+                    and (color is None or (np.shape(color) == col_l.shape and np.array_equal(color, col_l)))):
+                return
         idx, J = split_nbs(nbs)
         col = None if color is None else np.ascontiguousarray(color, dtype=np.int32)
         hsh = hashlib.blake2b(digest_size=16)
@@ -119,8 +129,11 @@ class Device:
         if col is not None:
             hsh.update(col.tobytes())
         key = (idx.shape, hsh.digest())
+        keep = (np.array(nbs, copy=True), None if color is None else np.array(color, copy=True))
         if key == self._graph_key:
+            self._graph_last = keep
             return
+        self._graph_last = None
         ncol = 0 if col is None else int(col.max()) + 1
         if col is not None and col.shape != (idx.shape[0],):
             raise ValueError("color must have one entry per spin")
@@ -129,6 +142,7 @@ class Device:
             self.nrows = self.lanes = 0
         self.nspins, self.maxnb, self.ncolors = idx.shape[0], idx.shape[1], ncol
         self._graph_key = key
+        self._graph_last = keep
 
     # ------------------------------------------------------------------ deterministic paths
     def qa_det(self, sched, mcsteps, slices, temp, spins, perms, rstates=None, uniforms=None):
@@ -374,6 +388,30 @@ class Device:
         check(lib.piqmc_results(self._h, _ptr(en), _ptr(words_out)))
         return (en.reshape(self.nrows * self.per_word, self.lanes // self.per_word),
                 self._unpack_replicas(words_out))
+
+    def qa_colour_results(self, sched, mcsteps, temp, seed, replica0=0, sweep0=0, trotter=0, orders=None,
+                          words_out=None):
+        """qa_colour + results as one library call: with the dataflow kernel the row chunks of the state are
+        staggered inside the launch and downloaded / reduced to energies as they finish, under the sweeps of
+        the others (piqmc_qa_colour_results).  Same return value as results()."""
+        sched = np.ascontiguousarray(sched, dtype=np.float64)
+        o = self._orders(orders, sched.size * int(mcsteps))
+        en = np.empty((self.nrows, self.lanes), dtype=np.float64)
+        if words_out is None:
+            words_out = np.empty((self.nspins, self.nrows), dtype=np.uint64)
+        elif (words_out.dtype != np.uint64 or not words_out.flags.c_contiguous
+              or words_out.shape != (self.nspins, self.nrows)):
+            raise ValueError("words_out must be C-contiguous uint64[nspins, nrows]")
+        check(lib.piqmc_qa_colour_results(self._h, _ptr(sched), sched.size, int(mcsteps), ctypes.c_float(temp),
+                                          int(seed), int(replica0), int(sweep0), int(trotter), _ptr(o), _ptr(en),
+                                          _ptr(words_out)))
+        return (en.reshape(self.nrows * self.per_word, self.lanes // self.per_word),
+                self._unpack_replicas(words_out))
+
+    @property
+    def pipelined_runs(self):
+        """calls of qa_colour_results that took the overlapped (staggered chunks) path"""
+        return int(lib.piqmc_pipelined_runs(self._h))
 
     def energy_histogram(self, e0=0.0, scale=1.0, lo=0.0, hi=1.0, nbins=64, reduce="mean"):
         """Histogram of (E - e0) * scale over the replicas of the last energy() / results() call, on the device

@@ -221,17 +221,24 @@ def QuantumAnnealReplicas(sched, mcsteps, slices, temp, nspins, spins0, nbs, see
         d.state_upload_spins(sp, tile=tile)
     t.append(time.perf_counter())
     d.set_global_moves(global_moves)
+    out = {"energies": None, "words": None}
+    fused = bool(energies and download and not carry)      # anneal + energies + download as one library call
     try:
         if carry:
             d.qa_carry(sched, int(mcsteps), temp, seed, replica0=replica0, orders=orders)
+        elif fused:
+            out["energies"], out["words"] = d.qa_colour_results(
+                sched, int(mcsteps), temp, seed, replica0=replica0, trotter=TROTTER[trotter], orders=orders,
+                words_out=words_out if S == 1 else None)
         else:
             d.qa_colour(sched, int(mcsteps), temp, seed, replica0=replica0, trotter=TROTTER[trotter],
                         orders=orders)
     finally:
         d.set_global_moves(False)
     t.append(time.perf_counter())
-    out = {"energies": None, "words": None}
-    if energies and download:
+    if fused:
+        t += [t[-1], t[-1]]
+    elif energies and download:
         out["energies"], out["words"] = d.results(words_out if S == 1 else None)
         t.append(time.perf_counter())
     else:

@@ -526,6 +526,45 @@ def test_config5_full_size_properties(dev):
     start = qmc.QuantumAnnealReplicas(sched[:0], 1, P, 0.01, n, None, nbs, 2024, color=color, nreplicas=64,
                                       device=dev)
     assert e_full.mean() < start["energies"].mean() - 0.5 * n
+    # bit-exact against the oracle at the bench shape (4096 rows: 8 row chunks x 4 passes per block, 511 levels,
+    # two sweeps in flight): the Philox key carries the global replica id, so single replicas of the full state
+    # can be restated on the CPU in isolation -- the reference's natural-order sequential sweep
+    # (piqmc/qmc.pyx:296-357), about 0.3 s per replica.  First / last row of a chunk, of a pass, of the state.
+    idx32, J32 = O.nbs_to_ell(nbs)
+    natural = np.tile(np.arange(n, dtype=np.int32), (steps, 1))
+    for r in (0, 127, 128, 511, 512, 2048, 3583, 4095):
+        _check_replica_against_oracle(w_full[r], sched, P, 0.01, idx32, J32, color, 2024, r, natural)
+    del full, w_full
+
+
+def _check_replica_against_oracle(words_r, sched, P, temp, idx32, J32, color, seed, r, orders):
+    import piqmc.tools as T
+    n = idx32.shape[0]
+    init = O.colour_init_spins(seed, r, 1, n)
+    want = np.repeat(init[:, :, None], P, axis=2).copy()
+    O.qa_colour(sched, 1, P, temp, idx32, J32, color, want, seed, replica0=r, orders=orders)
+    got = np.transpose(T.UnpackWords(words_r[None, :], P), (0, 2, 1))
+    assert np.array_equal(got, want), "replica %d differs from the oracle" % r
+
+
+@pytest.mark.parametrize("rows,replica0", [(512, 3584), (1024, 1024)])
+def test_config5_shard_shapes_bit_exact_vs_oracle(dev, rows, replica0):
+    """The per-GPU shapes of the 8- and 4-GPU runs of BASELINE configs[4] (512 / 1024 rows of the 256x256, P = 64
+    state: 4 row chunks of one / two passes per block), with the shard's global replica offset: sampled replicas
+    against the oracle's sequential natural-order sweep, bit for bit (piqmc/qmc.pyx:296-357)."""
+    import piqmc.qmc as qmc
+    import piqmc.tools as T
+    L, P, steps = 256, 64, 6
+    n = L * L
+    nbs, _ = T.GaussianTorusNeighbors(L, 2024)
+    color = T.TorusNaturalLevels(L)
+    sched = np.linspace(1.5, 1e-8, steps)
+    out = qmc.QuantumAnnealReplicas(sched, 1, P, 0.01, n, None, nbs, 2024, color=color, nreplicas=rows,
+                                    replica0=replica0, device=dev)
+    idx32, J32 = O.nbs_to_ell(nbs)
+    natural = np.tile(np.arange(n, dtype=np.int32), (steps, 1))
+    for k in (0, 127, 128, rows // 2 + 1, rows - 1):
+        _check_replica_against_oracle(out["words"][k], sched, P, 0.01, idx32, J32, color, 2024, replica0 + k, natural)
 
 
 # ------------------------------------------------------------------- several replicas per word
@@ -726,3 +765,57 @@ def test_qa_carry_residual_energy_distribution_vs_reference(golden, dev):
               % (name, _residual(a.mean(), "inst_0_32x32"), _residual(b.mean(), "inst_0_32x32"), p))
         assert p > 0.01
     assert _residual(mine.mean(), "inst_0_32x32") > 0.6
+
+
+# ------------------------------------------------------------------- anneal + results in one call
+@pytest.mark.parametrize("lag16", [None, 0, 8, 40, 100])
+@pytest.mark.parametrize("R,P,L", [(300, 8, 8), (1100, 64, 16)])
+def test_qa_colour_results_staggered_chunks(dev, monkeypatch, R, P, L, lag16):
+    """piqmc_qa_colour_results: the row chunks of the dataflow launch run staggered (chunk c lags c * lag16 / 16
+    sweeps), report to the host when they are final and are downloaded / reduced to energies while the others
+    still sweep.  Words and energies must equal the plain sequence qa_colour -> results bit for bit, for any
+    stagger (0, a fraction of a sweep, several sweeps, more than the run), and equal the oracle."""
+    import piqmc.tools as T
+    nbs, idx, J32, checker = _torus(L, 21)
+    n = L * L
+    steps = 5
+    sched = np.linspace(1.5, 1e-8, steps)
+    seed = 4242 + R
+    color = T.ColourGraph(nbs, "natural")
+    dev.set_variant(2)
+    try:
+        dev.set_graph(nbs, color)
+        dev.state_alloc(R, P)
+        dev.state_init_random(seed, 3, tile=True)
+        dev.qa_colour(sched, 1, 0.05, seed, replica0=3)
+        e_plain, w_plain = dev.results()
+        w_plain = w_plain.copy()
+        if lag16 is None:                                  # the library's own choice: no stagger below 16384 rows
+            monkeypatch.delenv("PIQMC_PIPE_LAG16", raising=False)
+        else:
+            monkeypatch.setenv("PIQMC_PIPE_LAG16", str(lag16))
+        dev.state_init_random(seed, 3, tile=True)
+        runs0 = dev.pipelined_runs
+        from piqmc import device as D
+        buf = D.pinned_empty((n, R), np.uint64)
+        e_pipe, w_pipe = dev.qa_colour_results(sched, 1, 0.05, seed, replica0=3, words_out=buf)
+        assert dev.pipelined_runs == runs0 + (0 if lag16 is None else 1), "the overlapped path was (not) taken"
+        runs0 = dev.pipelined_runs - 1
+        assert np.array_equal(w_pipe, w_plain)
+        assert np.array_equal(e_pipe, e_plain)
+        # and with the switch off: the same call runs the steps one after the other
+        monkeypatch.setenv("PIQMC_PIPE", "0")
+        dev.state_init_random(seed, 3, tile=True)
+        e_seq, w_seq = dev.qa_colour_results(sched, 1, 0.05, seed, replica0=3)
+        assert dev.pipelined_runs == runs0 + 1
+        assert np.array_equal(w_seq, w_plain) and np.array_equal(e_seq, e_plain)
+    finally:
+        dev.set_variant(0)
+    if lag16 in (None, 40):
+        for r in (0, R // 2, R - 1):
+            init = O.colour_init_spins(seed, 3 + r, 1, n)
+            want = np.repeat(init[:, :, None], P, axis=2).copy()
+            O.qa_colour(sched, 1, P, 0.05, idx, J32, checker, want, seed, replica0=3 + r,
+                        orders=np.tile(np.arange(n, dtype=np.int32), (steps, 1)))
+            got = np.transpose(T.UnpackWords(w_plain[r][None, :], P), (0, 2, 1))
+            assert np.array_equal(got, want)
