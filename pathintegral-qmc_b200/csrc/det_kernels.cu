@@ -7,6 +7,9 @@
 // the whole slice sweep (piqmc/qmc.pyx:134-135).  So these kernels run ONE REPLICA PER THREAD
 // and take their parallelism from the replica dimension only.  They are the parity path; the
 // throughput path is colour_kernels.cu.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace {
@@ -70,7 +73,8 @@ __device__ __forceinline__ bool exp_exceeds(double x, double u)
 // the uniform is k / (2^31 - 1) for an integer k: far below the cut (x < -22, nearly every rejected attempt at
 // the reference's T = 0.01) only k == 0 can accept, so neither the double division nor the exponential is
 // evaluated -- the decision is still exactly the one the full expression gives.
-__device__ __forceinline__ bool lazy_accept(Uniforms &us, float ediff, float temp)
+template <typename U>
+__device__ __forceinline__ bool lazy_accept(U &us, float ediff, float temp)
 {
     if (us.table == nullptr) {
         const int32_t k = us.g.next();
@@ -218,6 +222,172 @@ __global__ void __launch_bounds__(32) sa_det_kernel(
     if (consumed) consumed[r] = us.consumed;
 }
 
+// ---- the same two replays with the replica on chip ------------------------------------------------------
+// One warp per replica.  Spins (int8 [N][slices]), the ELL table, the sweep's visiting order and the libc
+// generator state live in shared memory; lane 0 walks the sequential chain (it cannot be parallelised, see the
+// header), all lanes move data in and out.  An attempt is then ~a hundred cycles of shared-memory latency and
+// dependent float adds instead of ~800 cycles of dependent global loads; the table row of the NEXT attempt is
+// fetched while the current one is decided (rows and orders never change, spins are read in program order).
+struct GlibcRandShared {
+    uint32_t *r;        // 31 words in shared memory
+    int f, b;
+    __device__ __forceinline__ int32_t next()
+    {
+        uint32_t v = (r[f] += r[b]);
+        f = (f + 1 == 31) ? 0 : f + 1;
+        b = (b + 1 == 31) ? 0 : b + 1;
+        return (int32_t)(v >> 1);
+    }
+};
+
+struct UniformsShared {
+    GlibcRandShared g;
+    const double *table;
+    uint64_t ntable;
+    unsigned long long consumed;
+    __device__ __forceinline__ double next()
+    {
+        double u;
+        if (table != nullptr)
+            u = (consumed < ntable) ? table[consumed] : 2.0;
+        else
+            u = (double)g.next() / 2147483647.0;
+        consumed++;
+        return u;
+    }
+};
+
+constexpr int DET_MAXNB = 8;          // table columns the on-chip kernels hold in registers (4 or 8)
+
+__host__ __device__ inline size_t det_smem_bytes(int nspins, int slices, int mnb, bool tables)
+{
+    // [offsets | -2J] | order | generator (36 words) | sign bytes of nspins + 1 rows (padded to 16)
+    return (tables ? (size_t)nspins * mnb * 8 : 0) + (size_t)nspins * 4 + 36 * 4 +
+           (((size_t)(nspins + 1) * slices + 15) & ~(size_t)15);
+}
+
+// QA: qmc.QuantumAnneal (piqmc/qmc.pyx:76-136): sched_tab = J_perp per schedule step, temp fixed.
+// !QA: sa.Anneal (piqmc/sa.pyx:80-120): sched_tab = temperature per schedule step, slices == 1.
+// The ELL table arrives transformed and padded to MNB columns (det_table, below): byte offset of the
+// neighbour's row of sign bytes (self entries and padding: a spare +1 row behind the last spin, so no compare
+// per attempt) and -2 J (exact; padding +0, which leaves the running sum as it is).  TSM: the table is copied
+// to shared memory too; otherwise it is read through L1 (larger lattices).
+template <bool QA, bool TSM, int MNB>
+__global__ void __launch_bounds__(32) det_onchip_kernel(
+    const float *__restrict__ sched_tab, int nsched, int mcsteps, int slices, float temp_qa, int nspins,
+    const int32_t *__restrict__ toff, const uint32_t *__restrict__ tm2j, int8_t *__restrict__ spins,
+    const int32_t *__restrict__ perms, piqmc_rand_state *rstate, const double *__restrict__ uniforms,
+    uint64_t nuniforms, unsigned long long *consumed)
+{
+    // Lane 0 walks the chain and one warp's issue rate bounds it, so every instruction per attempt counts: a
+    // spin is a sign byte (0x80 = -1) and the reference's term (-2 s_i)(J s_j) is one shift, one XOR on the
+    // sign bit of -2 J and the float add, in table order.
+    extern __shared__ __align__(16) unsigned char det_smem[];
+    int32_t *off_sm = reinterpret_cast<int32_t *>(det_smem);
+    uint32_t *m2J_sm = reinterpret_cast<uint32_t *>(off_sm + (TSM ? (size_t)nspins * MNB : 0));
+    int32_t *ord_s = reinterpret_cast<int32_t *>(m2J_sm + (TSM ? (size_t)nspins * MNB : 0));
+    uint32_t *gen_s = reinterpret_cast<uint32_t *>(ord_s + nspins);
+    uint8_t *sp = reinterpret_cast<uint8_t *>(gen_s + 36);         // [nspins + 1][slices]
+
+    const int r = blockIdx.x, lane = threadIdx.x;
+    const size_t nstate = (size_t)nspins * slices;
+    int8_t *s_glob = spins + (size_t)r * nstate;
+    const int32_t *perm_r = perms + (size_t)r * nsched * mcsteps * nspins;
+    if (TSM)
+        for (int e = lane; e < nspins * MNB; e += 32) {
+            off_sm[e] = toff[e];
+            m2J_sm[e] = tm2j[e];
+        }
+    for (size_t e = lane; e < nstate; e += 32) sp[e] = s_glob[e] < 0 ? (uint8_t)0x80 : (uint8_t)0;
+    for (int e = lane; e < slices; e += 32) sp[nstate + e] = 0;
+    if (!uniforms && lane < 31) gen_s[lane] = rstate[r].r[lane];
+    __syncwarp();
+
+    UniformsShared us;
+    us.g.r = gen_s;
+    us.g.f = uniforms ? 0 : rstate[r].f;
+    us.g.b = uniforms ? 0 : rstate[r].b;
+    us.table = uniforms ? uniforms + (size_t)r * nuniforms : nullptr;
+    us.ntable = nuniforms;
+    us.consumed = 0;
+
+    const int tleft = slices - 1, tright = 1;      // tidx is never assigned (qmc.pyx:83,115-117)
+    for (int ifield = 0; ifield < nsched; ifield++) {
+        const float par = sched_tab[ifield];        // J_perp (QA) or the temperature (SA) of this step
+        const uint32_t m2jp = __float_as_uint(-2.0f * par);
+        for (int step = 0; step < mcsteps; step++) {
+            const int32_t *perm = perm_r + (size_t)(ifield * mcsteps + step) * nspins;
+            for (int e = lane; e < nspins; e += 32) ord_s[e] = perm[e];
+            __syncwarp();
+            if (lane == 0) {
+                for (int k = 0; k < slices; k++) {
+                    float ediff = 0.0f;                          // QA: carried over the slice sweep (qmc.pyx:134-135)
+                    int nsidx;
+                    int4 noff[MNB / 4];
+                    uint4 nm2j[MNB / 4];
+                    const auto fetch = [&](int t) {              // the table row of attempt t
+                        nsidx = ord_s[t];
+#pragma unroll
+                        for (int v = 0; v < MNB / 4; v++) {
+                            if (TSM) {
+                                noff[v] = reinterpret_cast<const int4 *>(off_sm)[nsidx * (MNB / 4) + v];
+                                nm2j[v] = reinterpret_cast<const uint4 *>(m2J_sm)[nsidx * (MNB / 4) + v];
+                            } else {
+                                noff[v] = __ldg(reinterpret_cast<const int4 *>(toff) + nsidx * (MNB / 4) + v);
+                                nm2j[v] = __ldg(reinterpret_cast<const uint4 *>(tm2j) + nsidx * (MNB / 4) + v);
+                            }
+                        }
+                    };
+                    fetch(0);
+                    for (int t = 0; t < nspins; t++) {
+                        const int sidx = nsidx;
+                        int off[MNB];
+                        uint32_t m2j[MNB];
+#pragma unroll
+                        for (int v = 0; v < MNB / 4; v++) {
+                            off[4 * v] = noff[v].x; off[4 * v + 1] = noff[v].y; off[4 * v + 2] = noff[v].z; off[4 * v + 3] = noff[v].w;
+                            m2j[4 * v] = nm2j[v].x; m2j[4 * v + 1] = nm2j[v].y; m2j[4 * v + 2] = nm2j[v].z; m2j[4 * v + 3] = nm2j[v].w;
+                        }
+                        fetch((t + 1 < nspins) ? t + 1 : t);     // the next attempt's row, while this one is decided
+                        uint8_t *row = sp + sidx * slices;
+                        const uint32_t own = (uint32_t)row[k] << 24;
+                        if (!QA) ediff = 0.0f;                   // SA: per spin (sa.pyx:119)
+                        uint32_t oth[MNB];
+#pragma unroll
+                        for (int n = 0; n < MNB; n++)            // all neighbour reads in flight together
+                            oth[n] = (uint32_t)sp[off[n] + k] << 24;
+#pragma unroll
+                        for (int n = 0; n < MNB; n++)            // summed in table order (the reference's rounding)
+                            ediff = __fadd_rn(ediff, __uint_as_float(m2j[n] ^ own ^ oth[n]));
+                        bool flip;
+                        if (QA) {
+                            const uint32_t tl = (uint32_t)row[tleft] << 24, tr = (uint32_t)row[tright] << 24;
+                            ediff = __fadd_rn(ediff, __uint_as_float(m2jp ^ own ^ tl));
+                            ediff = __fadd_rn(ediff, __uint_as_float(m2jp ^ own ^ tr));
+                            flip = (ediff > 0.0f) ? true : lazy_accept(us, ediff, temp_qa);
+                        } else {
+                            flip = (ediff >= 0.0f) ? true : lazy_accept(us, ediff, par);     // >= (sa.pyx:114)
+                        }
+                        if (flip) row[k] = (uint8_t)((own >> 24) ^ 0x80u);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+    for (size_t e = lane; e < nstate; e += 32) s_glob[e] = (sp[e] & 0x80) ? (int8_t)-1 : (int8_t)1;
+    if (!uniforms) {
+        if (lane < 31) rstate[r].r[lane] = gen_s[lane];
+        us.g.f = __shfl_sync(0xffffffffu, us.g.f, 0);
+        us.g.b = __shfl_sync(0xffffffffu, us.g.b, 0);
+        if (lane == 0) {
+            rstate[r].f = us.g.f;
+            rstate[r].b = us.g.b;
+        }
+    }
+    if (consumed && lane == 0) consumed[r] = us.consumed;
+}
+
 // sa.Anneal_multispin, piqmc/sa.pyx:318-405.  One block of 64 threads per group of 64
 // replicas; thread k owns replica k = bit 63-k.  Sequential over attempts.
 __global__ void __launch_bounds__(64) sa_multispin_det_kernel(
@@ -269,11 +439,69 @@ __global__ void __launch_bounds__(64) sa_multispin_det_kernel(
 
 }  // namespace
 
+// the replica (spins, one visiting order, generator) fits in the shared memory of one block;
+// PIQMC_DET_ONCHIP=0 keeps the one-thread-per-replica kernels (testing)
+static int det_mnb(const piqmc_ctx *c) { return c->maxnb <= 4 ? 4 : 8; }
+
+static bool det_onchip_ok(const piqmc_ctx *c, int slices)
+{
+    if (const char *e = getenv("PIQMC_DET_ONCHIP"))
+        if (atoi(e) == 0) return false;
+    return c->maxnb >= 1 && c->maxnb <= DET_MAXNB && !c->h_idx.empty() &&
+           det_smem_bytes(c->nspins, slices, det_mnb(c), false) <= (size_t)200 * 1024;
+}
+
+// ... and the table with it, in a third of an SM's shared memory (three replicas per SM stay resident)
+static bool det_tables_fit(const piqmc_ctx *c, int slices)
+{
+    return det_smem_bytes(c->nspins, slices, det_mnb(c), true) <= (size_t)72 * 1024;
+}
+
+// One launch of the on-chip replay: the transformed table (see det_onchip_kernel) is built on the host from
+// the graph's host copy, lives in stream-ordered memory for the launch.
+template <bool QA>
+static int launch_det_onchip(piqmc_ctx *c, const float *d_sched, int nsched, int mcsteps, int slices, float temp,
+                             int nreplicas, int8_t *d_spins, const int32_t *d_perms, piqmc_rand_state *d_rstate,
+                             const double *d_uniforms, uint64_t nuniforms, unsigned long long *d_consumed)
+{
+    const int N = c->nspins, mnb = det_mnb(c);
+    std::vector<int32_t> off((size_t)N * mnb, N * slices);
+    std::vector<uint32_t> m2j((size_t)N * mnb, 0u);
+    for (int i = 0; i < N; i++)
+        for (int n = 0; n < c->maxnb; n++) {
+            const int j = c->h_idx[(size_t)i * c->maxnb + n];
+            const float v = -2.0f * c->h_J32[(size_t)i * c->maxnb + n];
+            off[(size_t)i * mnb + n] = (j == i) ? N * slices : j * slices;
+            memcpy(&m2j[(size_t)i * mnb + n], &v, 4);
+        }
+    int32_t *d_off = nullptr;
+    uint32_t *d_m2j = nullptr;
+    PIQMC_CUDA(cudaMallocAsync((void **)&d_off, off.size() * 4, c->stream));
+    PIQMC_CUDA(cudaMallocAsync((void **)&d_m2j, m2j.size() * 4, c->stream));
+    PIQMC_CUDA(cudaMemcpyAsync(d_off, off.data(), off.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    PIQMC_CUDA(cudaMemcpyAsync(d_m2j, m2j.data(), m2j.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    const bool tsm = det_tables_fit(c, slices);
+    const size_t smem = det_smem_bytes(N, slices, mnb, tsm);
+    auto kern = mnb == 4 ? (tsm ? det_onchip_kernel<QA, true, 4> : det_onchip_kernel<QA, false, 4>)
+                         : (tsm ? det_onchip_kernel<QA, true, 8> : det_onchip_kernel<QA, false, 8>);
+    PIQMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<nreplicas, 32, smem, c->stream>>>(d_sched, nsched, mcsteps, slices, temp, N, d_off, d_m2j, d_spins, d_perms,
+                                            d_rstate, d_uniforms, nuniforms, d_consumed);
+    c->launches++;
+    PIQMC_CUDA(cudaGetLastError());
+    PIQMC_CUDA(cudaFreeAsync(d_off, c->stream));
+    PIQMC_CUDA(cudaFreeAsync(d_m2j, c->stream));
+    return PIQMC_OK;
+}
+
 int launch_qa_det(piqmc_ctx *c, const float *d_jperp, int nsched, int mcsteps, int slices, float temp,
                   int nreplicas, int8_t *d_spins, const int32_t *d_perms, piqmc_rand_state *d_rstate,
                   const double *d_uniforms, uint64_t nuniforms, unsigned long long *d_consumed,
                   const double *d_dense, int dense_n)
 {
+    if (!d_dense && det_onchip_ok(c, slices))
+        return launch_det_onchip<true>(c, d_jperp, nsched, mcsteps, slices, temp, nreplicas, d_spins, d_perms, d_rstate,
+                                       d_uniforms, nuniforms, d_consumed);
     dim3 block(32), grid((nreplicas + 31) / 32);
     if (d_dense)
         qa_det_kernel<true><<<grid, block, 0, c->stream>>>(d_jperp, nsched, mcsteps, slices, temp, dense_n, 0,
@@ -294,6 +522,9 @@ int launch_sa_det(piqmc_ctx *c, const float *d_temps, int nsched, int mcsteps, i
                   const double *d_uniforms, uint64_t nuniforms, unsigned long long *d_consumed,
                   const double *d_dense, int dense_n)
 {
+    if (!d_dense && det_onchip_ok(c, 1))
+        return launch_det_onchip<false>(c, d_temps, nsched, mcsteps, 1, 0.0f, nreplicas, d_spins, d_perms, d_rstate,
+                                        d_uniforms, nuniforms, d_consumed);
     dim3 block(32), grid((nreplicas + 31) / 32);
     if (d_dense)
         sa_det_kernel<true><<<grid, block, 0, c->stream>>>(d_temps, nsched, mcsteps, dense_n, 0, nullptr, nullptr,

@@ -238,3 +238,40 @@ def test_energy_known_answers(golden, dev):
         J = _J(golden, inst)
         got = [sa.ClassicalIsingEnergy(s, J) for s in vec["energy_probe_spins_" + inst]]
         np.testing.assert_allclose(got, vec["energy_probe_" + inst], rtol=1e-12, atol=1e-12)
+
+
+# ------------------------------------------------------------------- on-chip replay kernels
+@pytest.mark.parametrize("inst,P,T,hot", [("inst_0_32x32", 20, 0.01, False), ("boixo16", 6, 0.5, True),
+                                          ("santoro_80x80", 20, 0.3, True)])
+def test_onchip_replay_equals_thread_per_replica(golden, dev, monkeypatch, inst, P, T, hot):
+    """The deterministic replays run one warp per replica with the replica in shared memory whenever it fits
+    (det_onchip_kernel); PIQMC_DET_ONCHIP=0 keeps the round-1 kernels (one thread per replica, global memory).
+    Same spins, same number of uniforms consumed, same libc generator state afterwards -- QA and SA, cold
+    (few draws) and hot (a draw at most attempts), with the libc generator and with a uniform table."""
+    from piqmc import device
+    vec = golden["vec"]
+    nbs = vec["nbs_" + inst]
+    n, R, steps = nbs.shape[0], 5, 4
+    sched = np.linspace(1.5, 1e-8, steps)
+    rng0 = np.random.RandomState(11)
+    spins = (2 * rng0.randint(2, size=(R, n, 1)) - 1).astype(np.int8).repeat(P, axis=2)
+    perms = np.stack([O.make_perms(np.random.RandomState(100 + r), n, steps * 2) for r in range(R)])
+    dev.set_graph(nbs)
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("PIQMC_DET_ONCHIP", mode)
+        a = spins.copy()
+        st = device.rand_states(range(R))
+        ca = dev.qa_det(sched, 2, P, T, a, perms, rstates=st)
+        b = spins[:, :, 0].copy()
+        st2 = device.rand_states(range(R))
+        temps = np.linspace(3.0 if hot else 0.3, 0.05, steps)
+        cb = dev.sa_det(temps, 2, b, perms, rstates=st2)
+        u = np.random.RandomState(5).rand(R, 2 * steps * n * P)
+        c = spins.copy()
+        cc = dev.qa_det(sched, 2, P, T, c, perms, uniforms=u)
+        out[mode] = (a, np.array(ca), np.frombuffer(bytes(st), dtype=np.uint8).copy(), b, np.array(cb),
+                     np.frombuffer(bytes(st2), dtype=np.uint8).copy(), c, np.array(cc))
+    for x, y in zip(out["1"], out["0"]):
+        assert np.array_equal(x, y)
+    assert out["1"][1].sum() > 0 and (not hot or out["1"][4].sum() > n)     # draws did happen
