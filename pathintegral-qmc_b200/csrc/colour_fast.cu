@@ -67,7 +67,9 @@ struct FastArgs {
 // MINB = resident blocks per SM the register allocation is capped for (7 -> 72 registers, 8 -> 64, 9 -> 56):
 // more resident blocks hide the per-unit latencies (ticket, record, flags) better, which matters
 // most when a unit has little work (few rows).
-template <bool QA, int TROT, int MINB, bool SEG = false>
+// PIPE: staggered row chunks with a completion signal per chunk (piqmc_qa_colour_results); a separate
+// instantiation, so that the plain kernel pays nothing for it.
+template <bool QA, int TROT, int MINB, bool SEG = false, bool PIPE = false>
 __global__ void __launch_bounds__(FAST_THREADS, MINB) colour_sweep_fast(const FastArgs a)
 {
     __shared__ SpinTable tab;
@@ -84,7 +86,7 @@ __global__ void __launch_bounds__(FAST_THREADS, MINB) colour_sweep_fast(const Fa
         const unsigned int t = atomicAdd(a.ticket, 1u) - a.ticket_base;
         const unsigned int per_sweep = (unsigned int)a.nspins * (unsigned int)a.nchunks;
         unsigned int q, rem, nact = (unsigned int)a.nchunks, clo = 0u;
-        if (t >= a.base_steady && t < a.base_down) {              // all chunks active (every ticket when lag16 == 0)
+        if (!PIPE || (t >= a.base_steady && t < a.base_down)) {   // all chunks active (every ticket when lag16 == 0)
             const unsigned int u = t - a.base_steady;
             q = u / per_sweep;
             rem = u - q * per_sweep;
@@ -115,7 +117,7 @@ __global__ void __launch_bounds__(FAST_THREADS, MINB) colour_sweep_fast(const Fa
     const int4 *rp = reinterpret_cast<const int4 *>(a.recs + (a.per_sweep_lists ? (size_t)q * a.nspins : 0) + m);
     const int4 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2);
     const int i = r0.x;
-    const int s = q - r0.y - ((chunk * a.lag16) >> 4);
+    const int s = q - r0.y - (PIPE ? ((chunk * a.lag16) >> 4) : 0);
     if (s < 0 || s >= a.nsweeps) return;                           // ramp-up / ramp-down periods
     const int nb[4] = {r0.z, r0.w, r1.x, r1.y};
     const float Jn[4] = {__int_as_float(r1.z), __int_as_float(r1.w), __int_as_float(r2.x), __int_as_float(r2.y)};
@@ -388,7 +390,7 @@ __global__ void __launch_bounds__(FAST_THREADS, MINB) colour_sweep_fast(const Fa
     __syncthreads();
     if (threadIdx.x == 0) {                                         // release orders the block's stores
         st_release(a.done + (size_t)i * a.nchunks + chunk, tag);   // (cumulative through the barrier)
-        if (a.chunk_count != nullptr && tag == a.tag0 + (uint32_t)a.nsweeps) {
+        if (PIPE && a.chunk_count != nullptr && tag == a.tag0 + (uint32_t)a.nsweeps) {
             // last sweep of the launch: count the spins of this row chunk that are final; the unit that completes
             // the chunk tells the host (fence; atomic = release, atomic; fence = acquire, both system-wide: the
             // copy engine then reads final words)
@@ -502,7 +504,8 @@ int launch_fast_sweeps(piqmc_ctx *c, int qa, int trotter, int nsweeps, const Piq
     a.chunk_count = nullptr;
     a.chunk_flag = nullptr;
     c->pipe_armed = 0;
-    if (c->pipe_request && nchunks <= c->pipe_chunk_cap && nchunks <= 255 && nsweeps <= max_sweeps) {
+    if (c->pipe_request && qa && !trotter && c->seg_S == 1 && nchunks <= c->pipe_chunk_cap && nchunks <= 255 &&
+        nsweeps <= max_sweeps) {              // (the one instantiation with the stagger code: QA, reference Trotter)
         // the stagger of the last chunk stays within the table size and within the periods of one chunk
         int lag16 = c->pipe_lag16;
         const int cap = std::min(FAST_MAX_LAG, nsweeps + nperiods_extra);
@@ -561,7 +564,8 @@ int launch_fast_sweeps(piqmc_ctx *c, int qa, int trotter, int nsweeps, const Piq
             if (minb == 7) colour_sweep_fast<true, 1, 7><<<grid, block, 0, c->stream>>>(a);
             else           colour_sweep_fast<true, 1, 8><<<grid, block, 0, c->stream>>>(a);
         } else {
-            if (c->seg_S > 1)    colour_sweep_fast<true, 0, 8, true><<<grid, block, 0, c->stream>>>(a);
+            if (c->pipe_armed)   colour_sweep_fast<true, 0, 9, false, true><<<grid, block, 0, c->stream>>>(a);
+            else if (c->seg_S > 1) colour_sweep_fast<true, 0, 8, true><<<grid, block, 0, c->stream>>>(a);
             else if (minb == 7)  colour_sweep_fast<true, 0, 7><<<grid, block, 0, c->stream>>>(a);
             else if (minb == 9)  colour_sweep_fast<true, 0, 9><<<grid, block, 0, c->stream>>>(a);
             else if (minb == 10) colour_sweep_fast<true, 0, 10><<<grid, block, 0, c->stream>>>(a);

@@ -272,7 +272,10 @@ __host__ __device__ inline size_t det_smem_bytes(int nspins, int slices, int mnb
 // neighbour's row of sign bytes (self entries and padding: a spare +1 row behind the last spin, so no compare
 // per attempt) and -2 J (exact; padding +0, which leaves the running sum as it is).  TSM: the table is copied
 // to shared memory too; otherwise it is read through L1 (larger lattices).
-template <bool QA, bool TSM, int MNB>
+// LIBC: the uniforms are the libc stream (the drop-in case): the generator runs one value ahead, the Metropolis
+// test of the two common outcomes (accept by sign; reject far below the cut with a non-zero integer uniform) is
+// branch-free, and only the rare attempt near the cut takes the exponential.  !LIBC: uniforms from a table.
+template <bool QA, bool TSM, int MNB, bool LIBC>
 __global__ void __launch_bounds__(32) det_onchip_kernel(
     const float *__restrict__ sched_tab, int nsched, int mcsteps, int slices, float temp_qa, int nspins,
     const int32_t *__restrict__ toff, const uint32_t *__restrict__ tm2j, int8_t *__restrict__ spins,
@@ -310,11 +313,28 @@ __global__ void __launch_bounds__(32) det_onchip_kernel(
     us.table = uniforms ? uniforms + (size_t)r * nuniforms : nullptr;
     us.ntable = nuniforms;
     us.consumed = 0;
+    // LIBC: glibc random_r() TYPE_3 (r[f] += r[b]; result r[f] >> 1), one value ahead: knext is the next
+    // rand(); gf / gb are where the value after it will come from, pf / pb where knext came from (the step is
+    // undone at the end if knext was never consumed, so the state goes back exactly as the reference leaves it)
+    int gf = us.g.f, gb = us.g.b, pf = 0, pb = 0;
+    uint32_t knext = 0u;
+    unsigned long long nconsumed = 0ull;
+    if (LIBC && lane == 0) {
+        pf = gf;
+        pb = gb;
+        const uint32_t v = (gen_s[gf] += gen_s[gb]);
+        knext = v >> 1;
+        gf = (gf + 1 == 31) ? 0 : gf + 1;
+        gb = (gb + 1 == 31) ? 0 : gb + 1;
+    }
 
     const int tleft = slices - 1, tright = 1;      // tidx is never assigned (qmc.pyx:83,115-117)
     for (int ifield = 0; ifield < nsched; ifield++) {
         const float par = sched_tab[ifield];        // J_perp (QA) or the temperature (SA) of this step
         const uint32_t m2jp = __float_as_uint(-2.0f * par);
+        // lazy_accept's cut: below it only the integer uniform 0 can accept
+        const float temp_now = QA ? temp_qa : par;
+        const float cut = (temp_now > 0.0f) ? -22.01f * temp_now : -__int_as_float(0x7f800000);
         for (int step = 0; step < mcsteps; step++) {
             const int32_t *perm = perm_r + (size_t)(ifield * mcsteps + step) * nspins;
             for (int e = lane; e < nspins; e += 32) ord_s[e] = perm[e];
@@ -359,14 +379,32 @@ __global__ void __launch_bounds__(32) det_onchip_kernel(
 #pragma unroll
                         for (int n = 0; n < MNB; n++)            // summed in table order (the reference's rounding)
                             ediff = __fadd_rn(ediff, __uint_as_float(m2j[n] ^ own ^ oth[n]));
-                        bool flip;
                         if (QA) {
                             const uint32_t tl = (uint32_t)row[tleft] << 24, tr = (uint32_t)row[tright] << 24;
                             ediff = __fadd_rn(ediff, __uint_as_float(m2jp ^ own ^ tl));
                             ediff = __fadd_rn(ediff, __uint_as_float(m2jp ^ own ^ tr));
-                            flip = (ediff > 0.0f) ? true : lazy_accept(us, ediff, temp_qa);
-                        } else {
-                            flip = (ediff >= 0.0f) ? true : lazy_accept(us, ediff, par);     // >= (sa.pyx:114)
+                        }
+                        const bool bysign = QA ? (ediff > 0.0f) : (ediff >= 0.0f);           // >= (sa.pyx:114)
+                        bool flip = bysign;
+                        if (LIBC) {
+                            // the value after knext, speculatively (committed only if knext is consumed now)
+                            const uint32_t v2 = gen_s[gf] + gen_s[gb];
+                            const int gf1 = (gf + 1 == 31) ? 0 : gf + 1, gb1 = (gb + 1 == 31) ? 0 : gb + 1;
+                            const uint32_t kk = knext;
+                            const bool consume = !bysign;
+                            if (consume) gen_s[gf] = v2;
+                            knext = consume ? (v2 >> 1) : knext;
+                            pf = consume ? gf : pf;
+                            pb = consume ? gb : pb;
+                            gf = consume ? gf1 : gf;
+                            gb = consume ? gb1 : gb;
+                            nconsumed += consume ? 1ull : 0ull;
+                            if (consume && !(ediff < cut && kk != 0u)) {                     // rare: near the cut, or k == 0
+                                const double ex = exp((double)__fdiv_rn(ediff, temp_now));
+                                flip = (ediff < cut) ? (ex > 0.0) : (ex > (double)(int32_t)kk / 2147483647.0);
+                            }
+                        } else if (!bysign) {
+                            flip = lazy_accept(us, ediff, temp_now);
                         }
                         if (flip) row[k] = (uint8_t)((own >> 24) ^ 0x80u);
                     }
@@ -376,16 +414,18 @@ __global__ void __launch_bounds__(32) det_onchip_kernel(
         }
     }
     for (size_t e = lane; e < nstate; e += 32) s_glob[e] = (sp[e] & 0x80) ? (int8_t)-1 : (int8_t)1;
-    if (!uniforms) {
-        if (lane < 31) rstate[r].r[lane] = gen_s[lane];
-        us.g.f = __shfl_sync(0xffffffffu, us.g.f, 0);
-        us.g.b = __shfl_sync(0xffffffffu, us.g.b, 0);
-        if (lane == 0) {
-            rstate[r].f = us.g.f;
-            rstate[r].b = us.g.b;
+    if (LIBC) {
+        if (lane == 0) {                      // knext was produced but not consumed: take the step back
+            gen_s[pf] -= gen_s[pb];
+            rstate[r].f = pf;
+            rstate[r].b = pb;
         }
+        __syncwarp();
+        if (lane < 31) rstate[r].r[lane] = gen_s[lane];
+        if (consumed && lane == 0) consumed[r] = nconsumed;
+    } else {
+        if (consumed && lane == 0) consumed[r] = us.consumed;
     }
-    if (consumed && lane == 0) consumed[r] = us.consumed;
 }
 
 // sa.Anneal_multispin, piqmc/sa.pyx:318-405.  One block of 64 threads per group of 64
@@ -482,8 +522,11 @@ static int launch_det_onchip(piqmc_ctx *c, const float *d_sched, int nsched, int
     PIQMC_CUDA(cudaMemcpyAsync(d_m2j, m2j.data(), m2j.size() * 4, cudaMemcpyHostToDevice, c->stream));
     const bool tsm = det_tables_fit(c, slices);
     const size_t smem = det_smem_bytes(N, slices, mnb, tsm);
-    auto kern = mnb == 4 ? (tsm ? det_onchip_kernel<QA, true, 4> : det_onchip_kernel<QA, false, 4>)
-                         : (tsm ? det_onchip_kernel<QA, true, 8> : det_onchip_kernel<QA, false, 8>);
+    auto kern = d_uniforms
+        ? (mnb == 4 ? (tsm ? det_onchip_kernel<QA, true, 4, false> : det_onchip_kernel<QA, false, 4, false>)
+                    : (tsm ? det_onchip_kernel<QA, true, 8, false> : det_onchip_kernel<QA, false, 8, false>))
+        : (mnb == 4 ? (tsm ? det_onchip_kernel<QA, true, 4, true> : det_onchip_kernel<QA, false, 4, true>)
+                    : (tsm ? det_onchip_kernel<QA, true, 8, true> : det_onchip_kernel<QA, false, 8, true>));
     PIQMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<nreplicas, 32, smem, c->stream>>>(d_sched, nsched, mcsteps, slices, temp, N, d_off, d_m2j, d_spins, d_perms,
                                             d_rstate, d_uniforms, nuniforms, d_consumed);
