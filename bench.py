@@ -333,7 +333,7 @@ def run_ours(args):
                 "overlapped_download": bool(pipelined),
                 "call": "qmc.QuantumAnnealReplicas(host int8 spins) -> host packed words + float64 energies; with "
                         "overlapped_download the row chunks of the one sweep launch finish staggered and are "
-                        "downloaded while the others still sweep ('sweeps' then covers sweeps + energies + download)"},
+                        "downloaded while the others still sweep (its breakdown then has no separate download figure)"},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": "colour_sweep_fast", "achieved": achieved, "peak": pk["hbm_gbs"],
                      "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],

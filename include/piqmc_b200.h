@@ -235,16 +235,19 @@ int piqmc_results(piqmc_handle h, double *energies, uint64_t *words);
 /* piqmc_qa_colour followed by piqmc_results, as one call -- what a caller of the reference's
  * qmc.QuantumAnneal_parallel gets back (the annealed configurations, piqmc/qmc.pyx:247-357) plus the
  * per-slice energies its drivers compute next (examples/spinglass32.py:150-160).  Same results as the two
- * calls; with the dataflow kernel and a static colouring the row chunks of the state (512 replicas each) are
- * staggered by a few sweeps inside the one launch, report to the host when they are final (mapped flags) and
- * are downloaded and reduced to energies while the remaining chunks still sweep, so that the host link works
- * under the anneal instead of after it.  words should be page-locked (piqmc_host_alloc) for the overlap.
- * Environment (tuning): PIQMC_PIPE=0 runs the steps one after the other; PIQMC_PIPE_LAG16 = stagger between
- * consecutive chunks in 1/16 sweeps.  piqmc_pipelined_runs: calls that took the overlapped path so far. */
+ * calls.  Opt-in (environment PIQMC_PIPE_LAG16 = stagger between consecutive row chunks in 1/16 sweeps): with the
+ * dataflow kernel and a static colouring the row chunks of the state (512 replicas each) are staggered inside the
+ * one launch, report to the host when they are final (mapped flags) and are downloaded while the remaining
+ * chunks still sweep (words should be page-locked, piqmc_host_alloc).  Same results bit for bit; measured on B200
+ * it does not end earlier than the plain sequence (profiles/r2_e2e_overlap.md section 1), which is therefore what
+ * the call runs by default.  piqmc_pipelined_runs: calls that took the overlapped path so far. */
 int piqmc_qa_colour_results(piqmc_handle h, const double *sched, int nsched, int mcsteps, float temp,
                             uint64_t seed, uint32_t replica0, uint32_t sweep0, int trotter,
                             const int32_t *orders, double *energies, uint64_t *words);
 uint64_t piqmc_pipelined_runs(piqmc_handle h);
+/* Host seconds the last piqmc_qa_colour_results spent in the sweeps and in energies + download (the second is ~0
+ * when the overlapped path ran: the downloads then happen inside the first). */
+int piqmc_last_phase_seconds(piqmc_handle h, double *sweeps, double *results);
 
 /* Histogram of the energies of the last piqmc_energy / piqmc_results on the device (the residual-energy
  * statistics of examples/santoro80.py:290-323 without moving R x slices doubles to the host): one value per

@@ -550,11 +550,15 @@ static int pipe_prepare(piqmc_ctx *h, int nchunks)
 // download per stagger), but the ramps at both ends of the run stay a fraction of it.  Measured on B200
 // (profiles/r2_e2e_overlap.md): a ticket period with few active rows is bound by its dependency chain and costs
 // as much as the download it hides (256x256 torus: 1.8 ms per period with one 512-row chunk active, 3.6 ms with
-// all 4096 rows), so staggering only pays when the ramps still hold thousands of rows: states of 16384+ rows.
+// all 4096 rows); with 16384 rows the ramps are cheap (sweeps 280 -> 299 ms at lag16 = 5) but the chunk-wise 2-D
+// copies next to the running kernel reach 31 GB/s against 57 GB/s for the one contiguous copy, and the call ends
+// later than the plain sequence (504 ms against 458 ms).  So the stagger is opt-in: PIQMC_PIPE_LAG16 (tests,
+// experiments); without it this returns 0 and the call runs the plain sequence.  The model below is what a
+// layout with contiguous chunks would use.
 static int pipe_choose_lag16(const piqmc_ctx *h, size_t nsweeps, int rpb, int nchunks)
 {
     if (const char *e = getenv("PIQMC_PIPE_LAG16")) return std::max(0, atoi(e));
-    if (nchunks < 2 || h->nrows < 16384) return 0;
+    if (nchunks < 2 || !getenv("PIQMC_PIPE_AUTO")) return 0;
     const double t_copy = (double)rpb * h->nspins * 8.0 / 43e9;                         // one chunk over the host link, GPU busy
     const double levels = (double)std::max(1, h->ncolors) / (double)(h->flow_extra + 1);
     const double t_period = std::max((double)h->nrows * h->nspins * 64.0 / 4.5e12,     // issue-bound sweep ...
@@ -1542,16 +1546,31 @@ int piqmc_qa_colour_results(piqmc_handle h, const double *sched, int nsched, int
     if (const char *e = getenv("PIQMC_PIPE")) h->pipe_request = atoi(e) != 0;
     h->pipe_energies = energies;
     h->pipe_words = words;
+    struct timespec t0, t1, t2;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
     const int rc = piqmc_qa_colour(h, sched, nsched, mcsteps, temp, seed, replica0, sweep0, trotter, orders);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
     const bool done = h->pipe_armed != 0;
     h->pipe_request = h->pipe_armed = 0;
     h->pipe_energies = nullptr;
     h->pipe_words = nullptr;
     if (rc != PIQMC_OK) return rc;
-    return done ? PIQMC_OK : piqmc_results(h, energies, words);
+    const int rc2 = done ? PIQMC_OK : piqmc_results(h, energies, words);
+    clock_gettime(CLOCK_MONOTONIC, &t2);
+    h->phase_s[0] = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);   // overlapped path: all of it
+    h->phase_s[1] = (double)(t2.tv_sec - t1.tv_sec) + 1e-9 * (double)(t2.tv_nsec - t1.tv_nsec);
+    return rc2;
 }
 
 uint64_t piqmc_pipelined_runs(piqmc_handle h) { return h ? h->pipe_runs : 0; }
+
+int piqmc_last_phase_seconds(piqmc_handle h, double *sweeps, double *results)
+{
+    PIQMC_REQUIRE(h != nullptr, PIQMC_EINVAL, "null handle");
+    if (sweeps) *sweeps = h->phase_s[0];
+    if (results) *results = h->phase_s[1];
+    return PIQMC_OK;
+}
 
 int piqmc_qa_carry(piqmc_handle h, const double *sched, int nsched, int mcsteps, float temp, uint64_t seed,
                    uint32_t replica0, uint32_t sweep0, const int32_t *orders)

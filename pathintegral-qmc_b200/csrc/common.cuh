@@ -176,6 +176,7 @@ struct piqmc_ctx {
     cudaStream_t aux_stream = nullptr;      // high priority: per-chunk energy reductions next to the running sweeps
     cudaEvent_t aux_event = nullptr;
     uint64_t pipe_runs = 0;         // calls that went through the pipelined path (reported to tests / bench)
+    double phase_s[2] = {0.0, 0.0};         // last piqmc_qa_colour_results: seconds in the sweeps / in energies + download
     double *pipe_energies = nullptr;        // host destinations of the call in flight
     uint64_t *pipe_words = nullptr;
 };

@@ -80,6 +80,7 @@ SIGNATURES = {
     "piqmc_qa_colour_results": (c_int, [c_void, c_void, c_int, c_int, c_f, c_u64, c_u32, c_u32, c_int, c_void,
                                         c_void, c_void]),
     "piqmc_pipelined_runs": (c_u64, [c_void]),
+    "piqmc_last_phase_seconds": (c_int, [c_void, c_void, c_void]),
     "piqmc_energy_histogram": (c_int, [c_void, c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                        c_int, c_void, c_void]),
     "piqmc_energy_coo": (c_int, [c_void, c_int, c_int, c_void, c_void, c_void, c_int, c_void, c_void]),

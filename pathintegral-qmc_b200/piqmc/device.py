@@ -408,6 +408,12 @@ class Device:
         return (en.reshape(self.nrows * self.per_word, self.lanes // self.per_word),
                 self._unpack_replicas(words_out))
 
+    def last_phase_seconds(self):
+        """(sweeps, energies + download) host seconds of the last qa_colour_results call"""
+        a, b = ctypes.c_double(0.0), ctypes.c_double(0.0)
+        check(lib.piqmc_last_phase_seconds(self._h, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
     @property
     def pipelined_runs(self):
         """calls of qa_colour_results that took the overlapped (staggered chunks) path"""

@@ -790,7 +790,7 @@ def test_qa_colour_results_staggered_chunks(dev, monkeypatch, R, P, L, lag16):
         dev.qa_colour(sched, 1, 0.05, seed, replica0=3)
         e_plain, w_plain = dev.results()
         w_plain = w_plain.copy()
-        if lag16 is None:                                  # the library's own choice: no stagger below 16384 rows
+        if lag16 is None:                                  # the library's own choice: the plain sequence (the stagger is opt-in)
             monkeypatch.delenv("PIQMC_PIPE_LAG16", raising=False)
         else:
             monkeypatch.setenv("PIQMC_PIPE_LAG16", str(lag16))
