@@ -384,7 +384,7 @@ def run_ours(args):
 
 
 def det_path_rates(dev):
-    """Throughput of the bit-exact replay kernels (one CUDA thread per replica: the reference's sequential
+    """Throughput of the bit-exact replay kernels (one warp per replica, the replica in shared memory: the reference's sequential
     algorithm with its own random streams) on BASELINE.json configs[1]: inst_0_32x32, P = 20, T = 0.01, 100
     schedule steps = 2.05e6 attempts per replica."""
     import piqmc.qmc as qmc
