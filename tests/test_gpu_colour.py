@@ -819,3 +819,33 @@ def test_qa_colour_results_staggered_chunks(dev, monkeypatch, R, P, L, lag16):
                         orders=np.tile(np.arange(n, dtype=np.int32), (steps, 1)))
             got = np.transpose(T.UnpackWords(w_plain[r][None, :], P), (0, 2, 1))
             assert np.array_equal(got, want)
+
+
+# ------------------------------------------------------------------- SA at the size of tools/bench_sa.py
+@pytest.mark.parametrize("hi,lo", [(3.0, 1.0), (0.3, 0.01)])
+def test_sa_bench_shape_bit_exact_vs_oracle(dev, hi, lo):
+    """The production SA path at the shape tools/bench_sa.py measures (256x256 Gaussian torus, 1024 rows = 65 536
+    replicas, natural-order levels), hot (about half of all lanes draw a uniform: the per-thread draw path with
+    the transposed pattern lookup, full warps) and cold: sampled word rows (64 replicas each) against the oracle's
+    sa.Anneal rules (piqmc/sa.pyx:95-120), bit for bit.  The oracle starts from the downloaded initial rows."""
+    import piqmc.tools as T
+    L, rows, steps = 256, 1024, 4
+    n = L * L
+    nbs, _ = T.GaussianTorusNeighbors(L, 2024)
+    color = T.TorusNaturalLevels(L)
+    idx32, J32 = O.nbs_to_ell(nbs)
+    sched = np.linspace(hi, lo, steps)
+    dev.set_graph(nbs, color)
+    dev.state_alloc(rows, 64)
+    dev.state_init_random(99, 0, tile=False)
+    start = dev.state_download_words().copy()                      # [rows, n]
+    dev.sa_colour(sched, 1, 99, row0=0)
+    final = dev.state_download_words()
+    lanes = np.arange(64, dtype=np.uint64)
+    natural = np.tile(np.arange(n, dtype=np.int32), (steps, 1))
+    for r in (0, 255, 256, 1023):
+        unpack = lambda w: (1 - 2 * ((w[None, :] >> lanes[:, None]) & np.uint64(1)).astype(np.int8)).astype(np.int8)
+        want = np.ascontiguousarray(unpack(start[r]))              # [64 replicas, n]
+        O.sa_colour(sched, 1, idx32, J32, color, want, seed=99, row0=r, orders=natural)
+        assert np.array_equal(unpack(final[r]), want), "row %d differs from the oracle" % r
+    assert not np.array_equal(start[0], final[0])
