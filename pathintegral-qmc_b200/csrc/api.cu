@@ -43,6 +43,9 @@ void free_graph(piqmc_ctx *c)
     free_dev(c->d_idx);
     free_dev(c->d_J32);
     free_dev(c->d_J64);
+    free_dev(c->d_fb_off);
+    free_dev(c->d_fb_j);
+    free_dev(c->d_fb_J);
     free_dev(c->d_idx_t);
     free_dev(c->d_J32_t);
     free_dev(c->d_members);
@@ -1042,6 +1045,30 @@ int piqmc_set_graph(piqmc_handle h, int nspins, int maxnb, const int32_t *idx, c
     PIQMC_CUDA(cudaMemcpy(h->d_J64, J, ne * sizeof(double), cudaMemcpyHostToDevice));
     PIQMC_CUDA(cudaMemcpy(h->d_idx_t, idxt.data(), ne * sizeof(int32_t), cudaMemcpyHostToDevice));
     PIQMC_CUDA(cudaMemcpy(h->d_J32_t, j32t.data(), ne * sizeof(float), cudaMemcpyHostToDevice));
+    {
+        // the entries the energy reduction adds: every stored key once (the row of its smaller index), fields as
+        // self entries; explicit zeros add +-0 and are left out
+        std::vector<int32_t> off(nspins + 1, 0), fj;
+        std::vector<double> fJ;
+        for (int i = 0; i < nspins; i++) {
+            for (int n = 0; n < maxnb; n++) {
+                const size_t e = (size_t)i * maxnb + n;
+                if (idx[e] >= i && J[e] != 0.0) {
+                    fj.push_back(idx[e]);
+                    fJ.push_back(J[e]);
+                }
+            }
+            off[i + 1] = (int32_t)fj.size();
+        }
+        PIQMC_CUDA(cudaMalloc(&h->d_fb_off, off.size() * sizeof(int32_t)));
+        PIQMC_CUDA(cudaMalloc(&h->d_fb_j, std::max<size_t>(fj.size(), 1) * sizeof(int32_t)));
+        PIQMC_CUDA(cudaMalloc(&h->d_fb_J, std::max<size_t>(fJ.size(), 1) * sizeof(double)));
+        PIQMC_CUDA(cudaMemcpy(h->d_fb_off, off.data(), off.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        if (!fj.empty()) {
+            PIQMC_CUDA(cudaMemcpy(h->d_fb_j, fj.data(), fj.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+            PIQMC_CUDA(cudaMemcpy(h->d_fb_J, fJ.data(), fJ.size() * sizeof(double), cudaMemcpyHostToDevice));
+        }
+    }
     h->nspins = nspins;
     h->maxnb = maxnb;
     h->h_idx.assign(idx, idx + ne);

@@ -104,7 +104,11 @@ struct piqmc_ctx {
     int nspins = 0, maxnb = 0, ncolors = 0;
     int32_t *d_idx = nullptr;       // [N][maxnb]  row-major, table order (deterministic kernels)
     float *d_J32 = nullptr;         // [N][maxnb]
-    double *d_J64 = nullptr;        // [N][maxnb]  (energy reduction)
+    double *d_J64 = nullptr;        // [N][maxnb]  exact reference values
+    // energy reduction: per spin the table entries that count (neighbour index >= own index, coupling != 0), in
+    // table order: offsets [N + 1], neighbour (own index for a field), coupling
+    int32_t *d_fb_off = nullptr, *d_fb_j = nullptr;
+    double *d_fb_J = nullptr;
     int32_t *d_idx_t = nullptr;     // [maxnb][N]  transposed, coalesced over spins (colour kernels)
     float *d_J32_t = nullptr;       // [maxnb][N]
     int32_t *d_members = nullptr;   // spins sorted by colour (static colouring)

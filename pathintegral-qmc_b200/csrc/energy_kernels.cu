@@ -7,46 +7,84 @@
 // neighbour index is larger than the row index; diagonal keys appear once as self-neighbours.
 // Summation order is fixed (no atomics): results are reproducible.  Padding entries (0, 0.0) of a
 // row i > 0 point at spin 0 < i and are skipped; those of row 0 add +-0.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
 
-constexpr int EN_ROWS = 32;     // rows per block: 8 warps x 4 rows
 constexpr int EN_THREADS = 256;
 
-// Thread = (row, group of 8 lanes): a warp covers 4 consecutive rows x 8 lane groups, so every
-// word load of a warp is one 32-byte sector (4 rows x 8 bytes, each broadcast to the 8 threads of
-// its row) and the table entries (idx, J) are warp-uniform.  grid = (row tiles, spin splits);
-// block (tile, sp) sums spins sp, sp + nsplit, ... for its 32 rows; 8 float64 accumulators per
-// thread, one per lane.  Fields and bonds go into the same sum: E = -(sum).
-__global__ void __launch_bounds__(EN_THREADS) energy_partial_kernel(
-    const uint64_t *__restrict__ words, int nspins, int nrows, int maxnb,
-    const int32_t *__restrict__ idx, const double *__restrict__ J, double *__restrict__ part, int row_lo, int row_hi)
+// Thread = (row, group of LPT lanes), LPT = 32 for states with many rows (a warp covers 16 consecutive rows: every
+// word load of a warp is 128 contiguous bytes) and 8 otherwise (4 rows x 8 lane groups per warp: more threads for
+// few rows).  grid = (row tiles, spin splits); block (tile, sp) sums spins sp, sp + nsplit, ... for its rows; LPT
+// float64 accumulators per thread, one per lane.  Fields and bonds go into the same sum: E = -(sum).
+// The entries come from the per-spin list of piqmc_set_graph (neighbour index >= own index, J != 0, table order);
+// two spins are in flight per iteration (their words and the first two neighbour words of each are requested
+// before the first add).  A lane accumulates D = the sum of J over its DISAGREEING entries -- one bit test and one
+// predicated DADD per (entry, lane) -- next to the lane-independent total T of all J; sum_b J_b s_i s_j = T - 2 D.
+// Measured on B200, 256x256 torus, 4096 rows x 64 lanes (3.4e10 adds): 13.9 / 13.2 / 12.0 ms with 8 / 16 / 32 lanes
+// per thread -- 2.9e12 float64 adds/s whatever the instruction count per add (8.9 warp-instructions per DADD in
+// the round-1 version, ~4.5 here): the reduction is bound by the rate of the float64 adder, not by loads or
+// issue slots; 512 rows: 2.6 -> 1.8 ms (fewer redundant loads).  The same float64 values for every LPT.
+template <int LPT>
+__device__ __forceinline__ void energy_add(double (&acc)[LPT], double &tot, double J, uint64_t x, int lg)
 {
-    const int lg = threadIdx.x & 7;
-    const int row = row_lo + blockIdx.x * EN_ROWS + (threadIdx.x >> 3);
+    const uint32_t bits = (LPT == 32) ? (uint32_t)(x >> (32 * lg)) : ((uint32_t)(x >> (LPT * lg)) & ((1u << LPT) - 1u));
+    tot += J;
+#pragma unroll
+    for (int b = 0; b < LPT; b++)        // (ptxas makes this an unconditional DADD into a temporary + two selects,
+        if ((bits >> b) & 1u) acc[b] += J;   //  also when the add is written as a predicated instruction)
+}
+
+template <int LPT>
+__global__ void __launch_bounds__(EN_THREADS) energy_partial_kernel(
+    const uint64_t *__restrict__ words, int nspins, int nrows, const int32_t *__restrict__ fb_off,
+    const int32_t *__restrict__ fb_j, const double *__restrict__ fb_J, double *__restrict__ part, int row_lo, int row_hi)
+{
+    constexpr int GROUPS = 64 / LPT;                    // threads per row
+    const int lg = threadIdx.x % GROUPS;
+    const int row = row_lo + blockIdx.x * (EN_THREADS / GROUPS) + threadIdx.x / GROUPS;
     const bool live = row < row_hi;
     const uint64_t *wrow = words + (live ? row : 0);   // word of spin s at wrow[s*nrows]
-    double acc[8];
+    double acc[LPT], tot = 0.0;
 #pragma unroll
-    for (int b = 0; b < 8; b++) acc[b] = 0.0;
-    for (int i = blockIdx.y; i < nspins; i += gridDim.y) {
-        const uint64_t w = wrow[(size_t)i * nrows];
-        for (int n = 0; n < maxnb; n++) {
-            const int j = idx[(size_t)i * maxnb + n];
-            if (j < i) continue;                              // the key is counted in row j
-            const long long jb = __double_as_longlong(J[(size_t)i * maxnb + n]);
-            const uint64_t x = (j == i) ? w : (w ^ wrow[(size_t)j * nrows]);
-            const uint32_t bits = (uint32_t)(x >> (8 * lg)) & 0xFFu;
+    for (int b = 0; b < LPT; b++) acc[b] = 0.0;
+    const int stride = (int)gridDim.y;
+    for (int i0 = blockIdx.y; i0 < nspins; i0 += 2 * stride) {
+        int sp[2], e0[2], e1[2];
+        uint64_t w[2], x[2][2];
 #pragma unroll
-            for (int b = 0; b < 8; b++)      // +J where the lane agrees (s_i s_j = +1), -J where it does not
-                acc[b] += __longlong_as_double(jb ^ ((long long)((bits >> b) & 1u) << 63));
+        for (int k = 0; k < 2; k++) {                   // all loads of both spins first
+            sp[k] = i0 + k * stride;
+            const bool on = sp[k] < nspins;
+            e0[k] = on ? fb_off[sp[k]] : 0;
+            e1[k] = on ? fb_off[sp[k] + 1] : 0;
+            w[k] = on ? wrow[(size_t)sp[k] * nrows] : 0ull;
+#pragma unroll
+            for (int t = 0; t < 2; t++) {
+                x[k][t] = 0ull;
+                if (e0[k] + t < e1[k]) {
+                    const int j = fb_j[e0[k] + t];
+                    x[k][t] = (j == sp[k]) ? 0ull : wrow[(size_t)j * nrows];
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 2; k++) {                   // then the adds, spin by spin, entry by entry
+#pragma unroll
+            for (int t = 0; t < 2; t++)
+                if (e0[k] + t < e1[k]) energy_add<LPT>(acc, tot, fb_J[e0[k] + t], w[k] ^ x[k][t], lg);
+            for (int e = e0[k] + 2; e < e1[k]; e++) {   // spins with more than two entries
+                const int j = fb_j[e];
+                energy_add<LPT>(acc, tot, fb_J[e], (j == sp[k]) ? w[k] : (w[k] ^ wrow[(size_t)j * nrows]), lg);
+            }
         }
     }
     if (live) {
-        double *p = part + ((size_t)blockIdx.y * nrows + row) * 64 + 8 * lg;
+        double *p = part + ((size_t)blockIdx.y * nrows + row) * 64 + LPT * lg;
 #pragma unroll
-        for (int b = 0; b < 8; b++) p[b] = acc[b];
+        for (int b = 0; b < LPT; b++) p[b] = tot - 2.0 * acc[b];
     }
 }
 
@@ -166,11 +204,22 @@ int energy_reserve(piqmc_ctx *c)
 int launch_energy_rows(piqmc_ctx *c, int row_lo, int count, cudaStream_t stream)
 {
     if (count <= 0) return PIQMC_OK;
-    const int tiles = (count + EN_ROWS - 1) / EN_ROWS;
     const int nsplit = energy_nsplit(c);
-    dim3 grid(tiles, nsplit);
-    energy_partial_kernel<<<grid, EN_THREADS, 0, stream>>>(c->d_words, c->nspins, c->nrows, c->maxnb, c->d_idx,
-                                                          c->d_J64, c->d_epart, row_lo, row_lo + count);
+    // the lane grouping depends on the size of the state, never on the row range of a launch: a replica's energy
+    // is the same float64 whichever rows are reduced together with it
+    int lpt = c->nrows >= 256 ? 32 : 8;
+    if (const char *e = getenv("PIQMC_ENERGY_LPT")) lpt = atoi(e);          // tuning knob: 8, 16 or 32 lanes per thread
+    const int rows_per_block = EN_THREADS / (64 / lpt);
+    dim3 grid((count + rows_per_block - 1) / rows_per_block, nsplit);
+    if (lpt == 32)
+        energy_partial_kernel<32><<<grid, EN_THREADS, 0, stream>>>(c->d_words, c->nspins, c->nrows, c->d_fb_off, c->d_fb_j,
+                                                                  c->d_fb_J, c->d_epart, row_lo, row_lo + count);
+    else if (lpt == 16)
+        energy_partial_kernel<16><<<grid, EN_THREADS, 0, stream>>>(c->d_words, c->nspins, c->nrows, c->d_fb_off, c->d_fb_j,
+                                                                  c->d_fb_J, c->d_epart, row_lo, row_lo + count);
+    else
+        energy_partial_kernel<8><<<grid, EN_THREADS, 0, stream>>>(c->d_words, c->nspins, c->nrows, c->d_fb_off, c->d_fb_j,
+                                                                 c->d_fb_J, c->d_epart, row_lo, row_lo + count);
     c->launches++;
     PIQMC_CUDA(cudaGetLastError());
     const int n = count * c->lanes;
