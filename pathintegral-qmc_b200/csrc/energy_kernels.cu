@@ -24,9 +24,11 @@ constexpr int EN_THREADS = 256;
 // before the first add).  A lane accumulates D = the sum of J over its DISAGREEING entries -- one bit test and one
 // predicated DADD per (entry, lane) -- next to the lane-independent total T of all J; sum_b J_b s_i s_j = T - 2 D.
 // Measured on B200, 256x256 torus, 4096 rows x 64 lanes (3.4e10 adds): 13.9 / 13.2 / 12.0 ms with 8 / 16 / 32 lanes
-// per thread -- 2.9e12 float64 adds/s whatever the instruction count per add (8.9 warp-instructions per DADD in
-// the round-1 version, ~4.5 here): the reduction is bound by the rate of the float64 adder, not by loads or
-// issue slots; 512 rows: 2.6 -> 1.8 ms (fewer redundant loads).  The same float64 values for every LPT.
+// per thread (8.9 warp-instructions per add in the round-1 version, ~4.5 here); 512 rows: 2.6 -> 1.8 ms (fewer
+// redundant loads).  A variant with 64-bit fixed-point accumulators (exact, order-independent sums) took 13.7 ms:
+// ncu there showed the integer / logic pipe 65 % busy at 49 % issue and 36 % of the stalls on loads with 4 warps
+// per scheduler (91 registers) -- no pipe is saturated, the loop is a mix of ALU rate and exposed load latency,
+// and it did not pay to change the arithmetic.  The same float64 values for every LPT.
 template <int LPT>
 __device__ __forceinline__ void energy_add(double (&acc)[LPT], double &tot, double J, uint64_t x, int lg)
 {
