@@ -51,6 +51,7 @@ void free_graph(piqmc_ctx *c)
     free_dev(c->d_members);
     free_dev(c->d_level);
     free_dev(c->d_recs);
+    free_dev(c->d_pate);
     free_dev(c->d_done);
     free_dev(c->d_cstat);
     free_dev(c->d_lstat);
@@ -174,6 +175,27 @@ static void build_unit_recs(const piqmc_ctx *h, const int32_t *level, const int3
     }
 }
 
+
+// The in-slice energy difference of every z-pattern of a unit's spin, summed in TABLE order with the float32
+// operations of pattern_energy (colour_device.cuh) -- it depends on the graph only, so the dataflow kernel
+// reads it next to the unit record instead of recomputing it in every unit (16 selects per table column).
+static void build_pattern_energies(const PiqmcUnitRec *recs, size_t n, float *out)
+{
+    for (size_t k = 0; k < n; k++) {
+        const PiqmcUnitRec &r = recs[k];
+        for (int p = 0; p < 16; p++) {
+            volatile float e = 0.0f;                 // every step rounded to float32, as __fadd_rn does
+            for (int col = 0; col < 4; col++)
+                for (int z = 0; z < 4; z++)
+                    if (((r.pad >> (2 * z)) & 3) == col) {
+                        float term = -2.0f * r.J[z];
+                        if (((p >> z) ^ (r.pad >> (8 + z))) & 1) term = -term;
+                        e = e + term;
+                    }
+            out[k * 16 + p] = e;
+        }
+    }
+}
 
 // ---- chain plan (chain_kernels.cu) -------------------------------------------------------------
 // The natural-order sweep of a 2-D lattice cut into chains of C consecutive spins.  Slot kinds of spin i
@@ -415,6 +437,9 @@ static int apply_colouring(piqmc_ctx *h, int ncolors, const int32_t *color, bool
         std::vector<PiqmcUnitRec> recs(h->nspins);
         build_unit_recs(h, color, pm.data(), po.data(), recs.data());
         PIQMC_CUDA(cudaMemcpy(h->d_recs, recs.data(), recs.size() * sizeof(PiqmcUnitRec), cudaMemcpyHostToDevice));
+        std::vector<float> pate(recs.size() * 16);
+        build_pattern_energies(recs.data(), recs.size(), pate.data());
+        PIQMC_CUDA(cudaMemcpy(h->d_pate, pate.data(), pate.size() * sizeof(float), cudaMemcpyHostToDevice));
         // level-synchronous kernel: where the steps of a period (members with the same level mod D) begin
         // in the period-major list
         const int Dp = std::min(D, ncolors);
@@ -734,7 +759,7 @@ static int run_colour_sweeps(piqmc_ctx *h, int qa, int trotter, int nsched, int 
                 if (nchunks <= 255 && (h->pipe_lag16 > 0 || getenv("PIQMC_PIPE_LAG16"))) TRY(pipe_prepare(h, nchunks));
                 else h->pipe_request = 0;
             }
-            TRY(launch_fast_sweeps(h, qa, trotter, (int)nsweeps, h->d_recs, h->flow_extra, 0, d_jp2.p, d_invT.p, seed,
+            TRY(launch_fast_sweeps(h, qa, trotter, (int)nsweeps, h->d_recs, h->d_pate, h->flow_extra, 0, d_jp2.p, d_invT.p, seed,
                                    row0, sweep0));
             if (h->pipe_armed) TRY(pipe_drain(h));
             // the per-sweep parameter arrays must outlive the launch
@@ -759,7 +784,9 @@ static int run_colour_sweeps(piqmc_ctx *h, int qa, int trotter, int nsched, int 
     DevBuf<int32_t> d_mem;
     DevBuf<PiqmcUnitRec> d_rec;
     DevBuf<int> d_soff, d_ssweep;
+    DevBuf<float> d_pate;
     if (wantrec) PIQMC_CUDA(d_rec.alloc(chunk * N));
+    if (fast) PIQMC_CUDA(d_pate.alloc(chunk * N * 16));
     else         PIQMC_CUDA(d_mem.alloc(chunk * N));
     std::vector<int32_t> members(chunk * N), levels(chunk * N);
     std::vector<PiqmcUnitRec> recs(wantrec ? chunk * N : 0);
@@ -804,7 +831,10 @@ static int run_colour_sweeps(piqmc_ctx *h, int qa, int trotter, int nsched, int 
         if (fast) {
             PIQMC_CUDA(cudaMemcpyAsync(d_rec.p, recs.data(), m * N * sizeof(PiqmcUnitRec), cudaMemcpyHostToDevice,
                                        h->stream));
-            TRY(launch_fast_sweeps(h, qa, trotter, (int)m, d_rec.p, 0, 1, d_jp2.p + base, d_invT.p + base, seed, row0,
+            std::vector<float> pate(m * N * 16);
+            build_pattern_energies(recs.data(), m * N, pate.data());
+            PIQMC_CUDA(cudaMemcpyAsync(d_pate.p, pate.data(), pate.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+            TRY(launch_fast_sweeps(h, qa, trotter, (int)m, d_rec.p, d_pate.p, 0, 1, d_jp2.p + base, d_invT.p + base, seed, row0,
                                    sweep0 + (uint32_t)base));
         } else {
             PIQMC_CUDA(cudaMemcpyAsync(d_mem.p, members.data(), m * N * sizeof(int32_t), cudaMemcpyHostToDevice,
@@ -1082,6 +1112,7 @@ int piqmc_set_graph(piqmc_handle h, int nspins, int maxnb, const int32_t *idx, c
     PIQMC_CUDA(cudaMalloc(&h->d_members, (size_t)nspins * sizeof(int32_t)));
     PIQMC_CUDA(cudaMalloc(&h->d_level, (size_t)nspins * sizeof(int32_t)));
     PIQMC_CUDA(cudaMalloc(&h->d_recs, (size_t)nspins * sizeof(PiqmcUnitRec)));
+    PIQMC_CUDA(cudaMalloc(&h->d_pate, (size_t)nspins * 16 * sizeof(float)));
     TRY(upload_level_stat(h));
     // integer couplings: the largest power of two q <= the smallest |J| such that every J32 is an integer
     // multiple of q with |multiple| <= 7 and row sums of at most 31 (bit-sliced resident kernel)

@@ -31,6 +31,7 @@ constexpr int FAST_MAX_LAG = 32;     // largest stagger of the last chunk, in ti
 struct FastArgs {
     uint64_t *words;            // [N][nrows]
     const PiqmcUnitRec *recs;   // per sweep (or shared): one record per member, in ticket order
+    const float *pate;          // [members][16] in-slice energy difference of every z-pattern, same order
     int nsweeps;                // sweeps covered by this launch
     const float *jp2, *invT;    // per sweep
     uint32_t *done;             // [N][nchunks] tag of the last finished sweep
@@ -116,6 +117,8 @@ __global__ void __launch_bounds__(FAST_THREADS, MINB) colour_sweep_fast(const Fa
     // of the member -> neighbour table -> level chain of dependent loads)
     const int4 *rp = reinterpret_cast<const int4 *>(a.recs + (a.per_sweep_lists ? (size_t)q * a.nspins : 0) + m);
     const int4 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2);
+    // the pattern energy of this lane (warps 0 .. NC-1 build the tables), requested together with the record
+    const float e0 = __ldg(a.pate + ((a.per_sweep_lists ? (size_t)q * a.nspins : 0) + m) * 16 + (threadIdx.x & 15));
     const int i = r0.x;
     const int s = q - r0.y - (PIPE ? ((chunk * a.lag16) >> 4) : 0);
     if (s < 0 || s >= a.nsweeps) return;                           // ramp-up / ramp-down periods
@@ -131,7 +134,7 @@ __global__ void __launch_bounds__(FAST_THREADS, MINB) colour_sweep_fast(const Fa
     //      are final (see the header comment); one barrier joins them
     const int warp = threadIdx.x >> 5;
     if (warp < NC) {
-        build_table_warp<QA>(tab, warp, Jn, pad, a.jp2[s], a.invT[s], a.force_generic != 0);
+        build_table_warp_pre<QA>(tab, warp, e0, Jn, pad, a.jp2[s], a.invT[s], a.force_generic != 0, QA && a.global_moves);
     } else if (warp == FAST_WARPS - 1) {
         const int ql = threadIdx.x & 31;
         if (ql <= 4) {
@@ -434,7 +437,7 @@ bool launch_fast_fits(const piqmc_ctx *c, int nperiods_extra)
 // Runs `nsweeps` sweeps in as few launches as the grid-size limit allows (normally one).
 // members/level: device arrays, level-major spin order and level per spin; either one list for
 // all sweeps or one per sweep.  d_jp2/d_invT: per sweep.
-int launch_fast_sweeps(piqmc_ctx *c, int qa, int trotter, int nsweeps, const PiqmcUnitRec *d_recs,
+int launch_fast_sweeps(piqmc_ctx *c, int qa, int trotter, int nsweeps, const PiqmcUnitRec *d_recs, const float *d_pate,
                        int nperiods_extra, int per_sweep_lists, const float *d_jp2, const float *d_invT,
                        uint64_t seed, uint32_t row0, uint32_t sweep0)
 {
@@ -519,6 +522,7 @@ int launch_fast_sweeps(piqmc_ctx *c, int qa, int trotter, int nsweeps, const Piq
     for (int s0 = 0; s0 < nsweeps; s0 += max_sweeps) {
         const int ns = std::min(max_sweeps, nsweeps - s0);
         a.recs = d_recs + (per_sweep_lists ? (size_t)s0 * c->nspins : 0);
+        a.pate = d_pate + (per_sweep_lists ? (size_t)s0 * c->nspins * 16 : 0);
         a.nsweeps = ns;
         a.jp2 = d_jp2 + s0;
         a.invT = d_invT + s0;

@@ -121,6 +121,7 @@ struct piqmc_ctx {
     float int_unit = 0.0f;          // 0: the graph does not qualify
     int8_t *d_iw = nullptr;         // [N][maxnb] signed weights
     PiqmcUnitRec *d_recs = nullptr; // unit records, spins sorted by (level mod D, level): period-major order
+    float *d_pate = nullptr;        // [N][16] in-slice energy difference of every z-pattern, same order (build_pattern_energies)
     int flow_extra = 0;             // ceil(ncolors / D) - 1 ramp periods
     // dataflow sweep kernel (colour_fast.cu)
     uint32_t *d_done = nullptr;     // [N][flow_nchunks] tag of the last finished sweep
@@ -274,7 +275,7 @@ int launch_energy_histogram(piqmc_ctx *c, int reduce, double e0, double scale, d
 int launch_energy_coo(piqmc_ctx *c, int nspins, int nnz, const int32_t *d_row, const int32_t *d_col,
                       const double *d_val, int nconfs, const int8_t *d_spins, double *d_out);
 // the production kernel: nsweeps sweeps in one dataflow launch (colour_fast.cu)
-int launch_fast_sweeps(piqmc_ctx *c, int qa, int trotter, int nsweeps, const PiqmcUnitRec *d_recs,
+int launch_fast_sweeps(piqmc_ctx *c, int qa, int trotter, int nsweeps, const PiqmcUnitRec *d_recs, const float *d_pate,
                        int nperiods_extra, int per_sweep_lists, const float *d_jp2, const float *d_invT,
                        uint64_t seed, uint32_t row0, uint32_t sweep0);
 bool launch_fast_fits(const piqmc_ctx *c, int nperiods_extra);   // the grid of one launch stays below 2^31 units
