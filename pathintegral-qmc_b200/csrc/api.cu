@@ -612,7 +612,11 @@ static int pipe_drain(piqmc_ctx *h)
     const bool trace = getenv("PIQMC_PIPE_TRACE") != nullptr && nchunks <= 64;
     const char *een = getenv("PIQMC_PIPE_ENERGY");
     const bool energy_at_end = !(een != nullptr && een[0] == 'c');
-    std::vector<cudaEvent_t> ev;
+    struct Events {                                  // released on every exit path
+        std::vector<cudaEvent_t> v;
+        ~Events() { for (auto &e : v) if (e) cudaEventDestroy(e); }
+    } evs;
+    std::vector<cudaEvent_t> &ev = evs.v;
     std::vector<double> seen(nchunks, 0.0);
     struct timespec ts0;
     clock_gettime(CLOCK_MONOTONIC, &ts0);
@@ -622,7 +626,7 @@ static int pipe_drain(piqmc_ctx *h)
         return 1e3 * (double)(ts.tv_sec - ts0.tv_sec) + 1e-6 * (double)(ts.tv_nsec - ts0.tv_nsec);
     };
     if (trace) {
-        ev.resize(1 + 4 * (size_t)nchunks);
+        ev.assign(1 + 4 * (size_t)nchunks, nullptr);
         for (auto &e : ev) PIQMC_CUDA(cudaEventCreate(&e));
         PIQMC_CUDA(cudaEventRecord(ev[0], h->copy_stream));
     }
@@ -678,7 +682,6 @@ static int pipe_drain(piqmc_ctx *h)
             fprintf(stderr, "[piqmc pipe]   chunk %d final at %.2f ms; download %.2f -> %.2f; energy %.2f -> %.2f\n", c,
                     seen[c], a, b, e0, e1);
         }
-        for (auto &e : ev) cudaEventDestroy(e);
     }
     h->pipe_runs++;
     return PIQMC_OK;

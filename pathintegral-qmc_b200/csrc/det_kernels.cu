@@ -517,9 +517,18 @@ static int launch_det_onchip(piqmc_ctx *c, const float *d_sched, int nsched, int
     int32_t *d_off = nullptr;
     uint32_t *d_m2j = nullptr;
     PIQMC_CUDA(cudaMallocAsync((void **)&d_off, off.size() * 4, c->stream));
-    PIQMC_CUDA(cudaMallocAsync((void **)&d_m2j, m2j.size() * 4, c->stream));
-    PIQMC_CUDA(cudaMemcpyAsync(d_off, off.data(), off.size() * 4, cudaMemcpyHostToDevice, c->stream));
-    PIQMC_CUDA(cudaMemcpyAsync(d_m2j, m2j.data(), m2j.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    if (cudaMallocAsync((void **)&d_m2j, m2j.size() * 4, c->stream) != cudaSuccess) {
+        cudaFreeAsync(d_off, c->stream);
+        piqmc_set_error("cudaMallocAsync of the replay table failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return PIQMC_ECUDA;
+    }
+    if (cudaMemcpyAsync(d_off, off.data(), off.size() * 4, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+        cudaMemcpyAsync(d_m2j, m2j.data(), m2j.size() * 4, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) {
+        cudaFreeAsync(d_off, c->stream);
+        cudaFreeAsync(d_m2j, c->stream);
+        piqmc_set_error("upload of the replay table failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return PIQMC_ECUDA;
+    }
     const bool tsm = det_tables_fit(c, slices);
     const size_t smem = det_smem_bytes(N, slices, mnb, tsm);
     auto kern = d_uniforms
@@ -531,9 +540,10 @@ static int launch_det_onchip(piqmc_ctx *c, const float *d_sched, int nsched, int
     kern<<<nreplicas, 32, smem, c->stream>>>(d_sched, nsched, mcsteps, slices, temp, N, d_off, d_m2j, d_spins, d_perms,
                                             d_rstate, d_uniforms, nuniforms, d_consumed);
     c->launches++;
-    PIQMC_CUDA(cudaGetLastError());
-    PIQMC_CUDA(cudaFreeAsync(d_off, c->stream));
-    PIQMC_CUDA(cudaFreeAsync(d_m2j, c->stream));
+    const cudaError_t launched = cudaGetLastError();
+    cudaFreeAsync(d_off, c->stream);                 // stream-ordered: behind the kernel, also when the launch failed
+    cudaFreeAsync(d_m2j, c->stream);
+    PIQMC_CUDA(launched);
     return PIQMC_OK;
 }
 
