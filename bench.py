@@ -38,7 +38,7 @@ B_ALG_HBM = 0.25        # bytes/attempt: each 64-slice word read once + written 
 B_ALG_SMEM = 1.0        # bytes/attempt touched on chip: own r+w, 4 neighbours, 2 Trotter bits
 # from the ncu captures under profiles/: measured DRAM traffic relative to the algorithmic bytes, and executed
 # warp-instructions per attempt, by rows per GPU (the kernel's per-unit overhead weighs more with few rows)
-NCU_CAPTURES = {4096: {"traffic_over_algorithmic": 1.006, "winst_per_attempt": 0.1787,
+NCU_CAPTURES = {4096: {"traffic_over_algorithmic": 1.006, "winst_per_attempt": 0.1569,
                        "source": "profiles/r2_colour_sweep_fast_ncu.md (4096 rows per GPU)"},
                 512: {"traffic_over_algorithmic": 1.002, "winst_per_attempt": 0.2985,
                       "source": "profiles/r2_colour_sweep_fast_ncu_512rows.md (512 rows per GPU)"}}
