@@ -295,6 +295,7 @@ __global__ void __launch_bounds__(FAST_THREADS, MINB) colour_sweep_fast(const Fa
             }
             uint64_t ACC = 0ull, NEED = 0ull, V = 0ull;
             uint32_t last = FID_NONE;                       // name of the function V holds
+            bool may_need = true;
             // Most word passes of a cold anneal have every lane of the warp in Trotter class 0 (the slices of a
             // replica agree): one vote, one evaluation, no loop (ncu: 1.4 populated classes per pass on average,
             // but three trips through the loop head).
@@ -303,6 +304,7 @@ __global__ void __launch_bounds__(FAST_THREADS, MINB) colour_sweep_fast(const Fa
                 V = eval_fn(fa, &tab.hacc[0], z);
                 ACC = V & C[0];
                 if (fb != FID_NONE) NEED = eval_fn(fb, &tab.hall[0], z) & ~V & C[0];
+                else may_need = false;                       // (block-uniform) no pattern of class 0 draws: no vote below
             } else
 #pragma unroll 1
             for (int c = 0; c < NC; c++) {
@@ -321,7 +323,7 @@ __global__ void __launch_bounds__(FAST_THREADS, MINB) colour_sweep_fast(const Fa
                 ACC |= V & Cc;
                 if (fb != FID_NONE) NEED |= eval_fn(fb, &tab.hall[c], z) & ~V & Cc;
             }
-            if (__any_sync(0xffffffffu, NEED != 0))
+            if (may_need && __any_sync(0xffffffffu, NEED != 0))
                 ACC |= resolve_draws<QA>(NEED, z, XL, XR, thr_tab, queue, (uint32_t)i, sweep, prow_warp, a.k0, a.k1,
                                          SEG ? a.seg_P : 64, SEG ? a.seg_S : 1);
             result = w ^ flip1 ^ ACC;
